@@ -1,0 +1,167 @@
+/*
+ * klujax_cuda.h — C-ABI of the B200 (sm_100a) twin of klujax's numeric hot path.
+ *
+ * Every entry point replaces one XLA-FFI handler of the reference
+ * (/root/reference/klujax.cpp; capsule export at :1386-1429, Python
+ * registration at /root/reference/klujax.py:834-1015).  The shapes are the
+ * canonical ones the reference's Python layer produces before binding
+ * (klujax.py:315-351, :1748-1849):
+ *     Ai, Aj : int32 [n_nz]              COO row / column indices
+ *     Ax     : T     [n_lhs, n_nz]       values, system-major
+ *     b, x   : T     [n_lhs, n_col, n_rhs]
+ * T = double (…_f64) or interleaved (re,im) double pairs (…_c128).
+ *
+ * Conventions
+ *  - "_dev" pointers are device memory on the current CUDA device, "_host"
+ *    pointers are host memory.  Numeric entry points only ENQUEUE work on
+ *    `stream` (a cudaStream_t passed as void*); they never synchronise, except
+ *    the first numeric call on a symbolic handle, which copies one seed system
+ *    to the host to fix the pivot sequence (see DESIGN.md "seeding").
+ *  - Return value: 0 = enqueued / done, otherwise a KLU status code (< 0) for
+ *    argument errors detected on the host; klujax_cuda_last_error() has text.
+ *  - Numerical failure is reported PER SYSTEM, on the device, KLU-style:
+ *    status_dev[m] = 0 (KLU_OK), 1 (KLU_SINGULAR: zero or non-finite pivot),
+ *    -3 (KLU_INVALID: index out of range / not in the analysed pattern);
+ *    growth_dev[m] = max |L(i,k)| of system m (pivot-parity certificate: KLU's
+ *    own threshold pivoting would have kept the static pivots while it stays
+ *    <= 1/tol = 1000).  Either pointer may be NULL.  The reference collapses
+ *    this into one ffi::Error for the whole batch (klujax.cpp:311-314); a
+ *    binding reproduces that by raising if any status != 0.
+ *  - Handles are opaque non-zero uint64 values, 0 = null, exactly like the
+ *    reference's pointer-as-u64 handles (klujax.cpp:395, :690, :1372).
+ *    A numeric handle array has one element per system; elements of one
+ *    `factor` call share device storage that is released when the last
+ *    element is freed (klujax.cpp:1282-1288 frees element by element).
+ */
+#ifndef KLUJAX_CUDA_H
+#define KLUJAX_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KLUJAX_CUDA_ABI_VERSION 1
+
+int klujax_cuda_abi_version(void);
+const char* klujax_cuda_last_error(void);
+
+/* ---- analyze / free_symbolic : klujax.cpp:1331-1374, :1293-1315 ---------- */
+int klujax_cuda_analyze(int n_col, int n_nz, const int32_t* Ai_host, const int32_t* Aj_host,
+                        uint64_t* symbolic_out);
+/* *freed_out: 1 = freed, 0 = nothing to free (null handle), like the i32 result */
+int klujax_cuda_free_symbolic(uint64_t symbolic, int32_t* freed_out);
+
+/* ---- solve_f64 / solve_c128 : klujax.cpp:251-380 ------------------------- */
+/* analyze + factor + solve + free in one call (indices on the host because the
+ * analysis runs there). */
+int klujax_cuda_solve_f64(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai_host,
+                          const int32_t* Aj_host, const double* Ax_dev, const double* b_dev,
+                          double* x_dev, int32_t* status_dev, double* growth_dev, void* stream);
+int klujax_cuda_solve_c128(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai_host,
+                           const int32_t* Aj_host, const double* Ax_dev, const double* b_dev,
+                           double* x_dev, int32_t* status_dev, double* growth_dev, void* stream);
+
+/* ---- solve_with_symbol_* : klujax.cpp:382-509 ; tsolve_with_symbol_* : :511-636
+ * Ai/Aj are DEVICE arrays here (they arrive as XLA buffers on every call and
+ * may be ordered differently from the analyze call, klujax.py:319-321).
+ * n_lhs_A / n_lhs_b may be 1 to broadcast against the other (klujax.py:1844-1848). */
+int klujax_cuda_solve_with_symbol_f64(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz,
+                                      const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                      const double* Ax_dev, const double* b_dev, double* x_dev,
+                                      int32_t* status_dev, double* growth_dev, void* stream);
+int klujax_cuda_solve_with_symbol_c128(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz,
+                                       const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                       const double* Ax_dev, const double* b_dev, double* x_dev,
+                                       int32_t* status_dev, double* growth_dev, void* stream);
+int klujax_cuda_tsolve_with_symbol_f64(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz,
+                                       const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                       const double* Ax_dev, const double* b_dev, double* x_dev,
+                                       int32_t* status_dev, double* growth_dev, void* stream);
+int klujax_cuda_tsolve_with_symbol_c128(uint64_t symbolic, int n_lhs, int n_col, int n_rhs,
+                                        int n_nz, const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                        const double* Ax_dev, const double* b_dev, double* x_dev,
+                                        int32_t* status_dev, double* growth_dev, void* stream);
+
+/* ---- factor_* : klujax.cpp:638-731 --------------------------------------- */
+/* numeric_out_host[n_lhs] receives the handles (host array: see INTEGRATION.md). */
+int klujax_cuda_factor_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai_dev,
+                           const int32_t* Aj_dev, const double* Ax_dev, uint64_t* numeric_out_host,
+                           int32_t* status_dev, double* growth_dev, void* stream);
+int klujax_cuda_factor_c128(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai_dev,
+                            const int32_t* Aj_dev, const double* Ax_dev, uint64_t* numeric_out_host,
+                            int32_t* status_dev, double* growth_dev, void* stream);
+
+/* ---- refactor_* : klujax.cpp:733-833 (in place; output handles = input handles) */
+int klujax_cuda_refactor_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai_dev,
+                             const int32_t* Aj_dev, const double* Ax_dev,
+                             const uint64_t* numeric_in_host, uint64_t* numeric_out_host,
+                             int32_t* status_dev, double* growth_dev, void* stream);
+int klujax_cuda_refactor_c128(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai_dev,
+                              const int32_t* Aj_dev, const double* Ax_dev,
+                              const uint64_t* numeric_in_host, uint64_t* numeric_out_host,
+                              int32_t* status_dev, double* growth_dev, void* stream);
+
+/* ---- refactor_and_solve_* : klujax.cpp:835-993 --------------------------- */
+int klujax_cuda_refactor_and_solve_f64(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz,
+                                       const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                       const double* Ax_dev, const double* b_dev,
+                                       const uint64_t* numeric_in_host, double* x_dev,
+                                       uint64_t* numeric_out_host, int32_t* status_dev,
+                                       double* growth_dev, void* stream);
+int klujax_cuda_refactor_and_solve_c128(uint64_t symbolic, int n_lhs, int n_col, int n_rhs,
+                                        int n_nz, const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                        const double* Ax_dev, const double* b_dev,
+                                        const uint64_t* numeric_in_host, double* x_dev,
+                                        uint64_t* numeric_out_host, int32_t* status_dev,
+                                        double* growth_dev, void* stream);
+
+/* ---- solve_with_numeric_* : klujax.cpp:995-1137 ; tsolve_with_numeric_* : :1139-1271
+ * b is canonical [n_lhs_b, n_col, n_rhs]; n_numeric or n_lhs_b may be 1 and is
+ * then broadcast (klujax.cpp:1044-1059); x is [max(n_numeric, n_lhs_b), n_col, n_rhs]. */
+int klujax_cuda_solve_with_numeric_f64(uint64_t symbolic, int n_numeric,
+                                       const uint64_t* numeric_host, int n_lhs_b, int n_col,
+                                       int n_rhs, const double* b_dev, double* x_dev, void* stream);
+int klujax_cuda_solve_with_numeric_c128(uint64_t symbolic, int n_numeric,
+                                        const uint64_t* numeric_host, int n_lhs_b, int n_col,
+                                        int n_rhs, const double* b_dev, double* x_dev, void* stream);
+int klujax_cuda_tsolve_with_numeric_f64(uint64_t symbolic, int n_numeric,
+                                        const uint64_t* numeric_host, int n_lhs_b, int n_col,
+                                        int n_rhs, const double* b_dev, double* x_dev, void* stream);
+int klujax_cuda_tsolve_with_numeric_c128(uint64_t symbolic, int n_numeric,
+                                         const uint64_t* numeric_host, int n_lhs_b, int n_col,
+                                         int n_rhs, const double* b_dev, double* x_dev,
+                                         void* stream);
+
+/* ---- free_numeric : klujax.cpp:1273-1291 --------------------------------- */
+int klujax_cuda_free_numeric(int n, const uint64_t* numeric_host, int32_t* freed_out);
+
+/* ---- dot_f64 / dot_c128 : klujax.cpp:165-249 (batched COO SpMM, "next" row f1) */
+int klujax_cuda_dot_f64(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai_dev,
+                        const int32_t* Aj_dev, const double* Ax_dev, const double* x_dev,
+                        double* b_dev, void* stream);
+int klujax_cuda_dot_c128(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai_dev,
+                         const int32_t* Aj_dev, const double* Ax_dev, const double* x_dev,
+                         double* b_dev, void* stream);
+
+/* ---- host-only introspection (used by the parity tests; no GPU needed) ---- */
+/* Fixes the pivot sequence from one host-resident system of values given in the
+ * COO order of the analyze call (what the first numeric call does internally). */
+int klujax_cuda_seed_host(uint64_t symbolic, int is_complex, const double* Ax_host);
+/* sizes: out[0]=n out[1]=nblocks out[2]=maxblock out[3]=nzoff out[4]=structural_rank
+ *        out[5]=nnz(L) strictly lower  out[6]=nnz(U) strictly upper  out[7]=seeded(0/1)
+ *        out[8]=regime (0 shared-memory, 1 level-scheduled)  out[9]=levels of factor+solve
+ *        out[10]=multiply-adds of one refactor  out[11]=noffdiag */
+int klujax_cuda_symbolic_info(uint64_t symbolic, int is_complex, int64_t* out12);
+/* P[n], Q[n], R[nblocks+1] of the analysis; any pointer may be NULL */
+int klujax_cuda_symbolic_perm(uint64_t symbolic, int32_t* P, int32_t* Q, int32_t* R);
+/* after seeding: Pnum[n]; CSC patterns of L and U in pivot order with block-local,
+ * ascending row indices (Lp/Up have n+1 entries) */
+int klujax_cuda_symbolic_pattern(uint64_t symbolic, int is_complex, int32_t* Pnum, int32_t* Lp,
+                                 int32_t* Li, int32_t* Up, int32_t* Ui);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KLUJAX_CUDA_H */

@@ -1,0 +1,461 @@
+// kernels_level.cuh — level-scheduled regime (K1, K3, K4, K5, K6, K7) for
+// matrices whose factors do not fit in shared memory.
+//
+// Layout in HBM: values are batch-interleaved, V[slot][system] (and
+// X[row][system*n_rhs + column] for the solves), so consecutive threads handle
+// consecutive systems / right-hand sides and every load of a value is
+// coalesced.  One persistent cooperative kernel walks the level sets of the
+// static task DAG (plan.hpp) with a grid-wide barrier between levels; there is
+// no sparsity logic on the device, only index lists shared by the whole batch.
+//
+// Replaces klu_refactor / klu_solve / klu_tsolve as called per system at
+// /root/reference/klujax.cpp:781, :911, :1087, :1220 and the b/x transposes at
+// :1069-1076, :1095-1101 (there is no transposition pass here: the
+// permutations P, Q and the row scaling are folded into the load and the store
+// of X).  Also holds the batched COO SpMM twin of dot_* (klujax.cpp:165-249).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "kernels_small.cuh"
+#include "plan.hpp"
+
+namespace kb {
+
+struct LevelProg {
+    int ntasks = 0, nlevels = 0;
+    int *d_out = nullptr, *d_div = nullptr, *d_pbeg = nullptr, *d_plen = nullptr, *d_kind = nullptr;
+    int *d_pa = nullptr, *d_pb = nullptr, *d_level_ptr = nullptr;
+    int max_level_tasks = 0;
+    int64_t n_mac = 0;
+    ~LevelProg() {
+        for (int* p : {d_out, d_div, d_pbeg, d_plen, d_kind, d_pa, d_pb, d_level_ptr})
+            if (p) cudaFree(p);
+    }
+    bool upload(const SlotLayout& lay, const TaskProgram& tp, std::string& err) {
+        (void)lay;
+        ntasks = static_cast<int>(tp.tasks.size());
+        nlevels = tp.nlevels;
+        n_mac = tp.n_mac;
+        std::vector<int> out(ntasks), dv(ntasks), pbeg(ntasks), plen(ntasks), kind(ntasks);
+        for (int t = 0; t < ntasks; ++t) {
+            out[t] = tp.tasks[t].out;
+            dv[t] = tp.tasks[t].div;
+            pbeg[t] = tp.tasks[t].pbeg;
+            plen[t] = tp.tasks[t].plen;
+            kind[t] = tp.tasks[t].kind;
+        }
+        for (int l = 0; l < nlevels; ++l)
+            max_level_tasks = std::max(max_level_tasks, tp.level_ptr[l + 1] - tp.level_ptr[l]);
+        auto up = [&](int** d, const std::vector<int>& v) {
+            const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(int);
+            if (cudaMalloc(reinterpret_cast<void**>(d), bytes) != cudaSuccess) return false;
+            return v.empty() ||
+                   cudaMemcpy(*d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+        };
+        if (!up(&d_out, out) || !up(&d_div, dv) || !up(&d_pbeg, pbeg) || !up(&d_plen, plen) ||
+            !up(&d_kind, kind) || !up(&d_pa, tp.pa) || !up(&d_pb, tp.pb) ||
+            !up(&d_level_ptr, tp.level_ptr)) {
+            err = "level program upload failed (out of device memory?)";
+            return false;
+        }
+        return true;
+    }
+};
+
+struct LevelCall {
+    int mode = 0, L = 0, r = 0, nz = 0, n = 0, n_val = 0, is_complex = 0, num_sms = 148, Lstore = 0;
+    const void* Ax = nullptr;
+    long long ax_stride = 0;
+    const void* b = nullptr;
+    long long b_stride = 0;
+    void* x = nullptr;
+    const int *coo_dst = nullptr, *pattern_bad = nullptr, *rs_ptr = nullptr, *rs_slot = nullptr;
+    const int *pnum = nullptr, *q = nullptr, *sysidx = nullptr;
+    int32_t* status = nullptr;
+    double* growth = nullptr;
+    void* V = nullptr;   // [n_val][lpad]
+    double* Rs = nullptr;  // [n][lpad]
+    long long lpad = 0;
+    cudaStream_t st = nullptr;
+};
+
+// ---- grid-wide barrier for the persistent kernels (cooperative launch) ----
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned nblocks, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nblocks;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// scatter Ax[m][e] -> V[slot][sys]; V has been zeroed
+template <typename T>
+__global__ void lv_scatter(int L, int nz, const typename Sc<T>::V* __restrict__ Ax,
+                           long long ax_stride, const int* __restrict__ coo_dst,
+                           const int* __restrict__ sysidx, typename Sc<T>::V* __restrict__ V,
+                           long long lpad) {
+    // 32 x 32 tile through shared memory: read along e, write along the system axis
+    __shared__ typename Sc<T>::V tile[32][33];
+    const int e0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    for (int dm = threadIdx.y; dm < 32; dm += blockDim.y) {
+        const int e = e0 + threadIdx.x, m = m0 + dm;
+        if (e < nz && m < L) tile[dm][threadIdx.x] = Ax[(long long)m * ax_stride + e];
+    }
+    __syncthreads();
+    for (int de = threadIdx.y; de < 32; de += blockDim.y) {
+        const int e = e0 + de, m = m0 + threadIdx.x;
+        if (e < nz && m < L) {
+            const int d = __ldg(coo_dst + e);
+            const int sm = sysidx ? sysidx[m] : m;
+            if (d >= 0) V[(long long)d * lpad + sm] = tile[threadIdx.x][de];
+        }
+    }
+}
+
+template <typename T>
+__global__ void lv_zero_slots(int L, int n_val, const int* __restrict__ sysidx,
+                              typename Sc<T>::V* __restrict__ V, long long lpad) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n_val * L;
+    for (long long i = tid; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = static_cast<int>(i % L);
+        const long long s = i / L;
+        V[s * lpad + (sysidx ? sysidx[m] : m)] = Sc<T>::zero();
+    }
+}
+
+// max-abs row scale factors and scaling, thread per (row, system)
+template <typename T>
+__global__ void lv_rowscale(int L, int n, const int* __restrict__ rs_ptr,
+                            const int* __restrict__ rs_slot, const int* __restrict__ sysidx,
+                            typename Sc<T>::V* __restrict__ V, double* __restrict__ Rs,
+                            long long lpad) {
+    using S = Sc<T>;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)n * L) return;
+    const int m = static_cast<int>(tid % L), i = static_cast<int>(tid / L);
+    const int sm = sysidx ? sysidx[m] : m;
+    const int pb = rs_ptr[i], pe = rs_ptr[i + 1];
+    double mx = 0.0;
+    for (int p = pb; p < pe; ++p) mx = fmax(mx, S::mag(V[(long long)rs_slot[p] * lpad + sm]));
+    if (mx == 0.0) mx = 1.0;
+    Rs[(long long)i * lpad + sm] = mx;
+    for (int p = pb; p < pe; ++p) {
+        typename S::V* q = V + (long long)rs_slot[p] * lpad + sm;
+        *q = S::rdiv(*q, mx);
+    }
+}
+
+struct LvArgs {
+    const int *out, *div, *pbeg, *plen, *kind, *pa, *pb, *level_ptr;
+    int nlevels, n_val, L, r;
+    long long lpad, Q;   // Q = L * r right-hand-side columns in the solve
+    void* V;
+    void* X;
+    const int* sysidx;
+    unsigned* barrier;
+    int* bad;                       // [L] OR of singular pivots
+    unsigned long long* growth2;    // [L] max |L|^2 as ordered bits
+};
+
+// Persistent refactorization: thread per (task, system) inside a level.
+template <typename T>
+__global__ void __launch_bounds__(256) lv_factor(const LvArgs a) {
+    using S = Sc<T>;
+    using V_t = typename S::V;
+    V_t* V = static_cast<V_t*>(a.V);
+    unsigned target = 0;
+    const int lanes = (a.L + 31) & ~31;  // systems padded to warps
+    for (int l = 0; l < a.nlevels; ++l) {
+        const int tb = __ldg(a.level_ptr + l), te = __ldg(a.level_ptr + l + 1);
+        const long long items = (long long)(te - tb) * lanes;
+        for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+             it += (long long)gridDim.x * blockDim.x) {
+            const int t = tb + static_cast<int>(it / lanes), m = static_cast<int>(it % lanes);
+            if (m >= a.L) continue;
+            const int sm = a.sysidx ? a.sysidx[m] : m;
+            const int pbeg = __ldg(a.pbeg + t), plen = __ldg(a.plen + t);
+            V_t acc = S::zero();
+#pragma unroll 4
+            for (int p = 0; p < plen; ++p) {
+                const V_t x = __ldcg(V + (long long)__ldg(a.pa + pbeg + p) * a.lpad + sm);
+                const V_t y = __ldcg(V + (long long)__ldg(a.pb + pbeg + p) * a.lpad + sm);
+                S::fma_acc(acc, x, y);
+            }
+            const int kind = __ldg(a.kind + t);
+            V_t* o = V + (long long)__ldg(a.out + t) * a.lpad + sm;
+            V_t v = S::sub(__ldcg(o), acc);
+            if (kind == TK_RECIP) {
+                if (S::bad_pivot(v)) a.bad[m] = 1;
+                v = S::recip(v);
+            } else if (kind >= TK_MUL) {
+                v = S::mul(v, __ldcg(V + (long long)__ldg(a.div + t) * a.lpad + sm));
+                if (kind == TK_MUL_TRACK)
+                    atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v)));
+            }
+            *o = v;
+        }
+        if (l + 1 < a.nlevels) grid_barrier(a.barrier, gridDim.x, target);
+    }
+}
+
+// Persistent triangular solves: thread per (task, right-hand-side column).
+template <typename T>
+__global__ void __launch_bounds__(256) lv_solve(const LvArgs a) {
+    using S = Sc<T>;
+    using V_t = typename S::V;
+    const V_t* V = static_cast<const V_t*>(a.V);
+    V_t* X = static_cast<V_t*>(a.X);
+    unsigned target = 0;
+    const long long lanes = (a.Q + 31) & ~31LL;
+    for (int l = 0; l < a.nlevels; ++l) {
+        const int tb = __ldg(a.level_ptr + l), te = __ldg(a.level_ptr + l + 1);
+        const long long items = (long long)(te - tb) * lanes;
+        for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+             it += (long long)gridDim.x * blockDim.x) {
+            const int t = tb + static_cast<int>(it / lanes);
+            const long long q = it % lanes;
+            if (q >= a.Q) continue;
+            const int m = static_cast<int>(q / a.r);
+            const int sm = a.sysidx ? a.sysidx[m] : m;
+            const int pbeg = __ldg(a.pbeg + t), plen = __ldg(a.plen + t);
+            V_t acc = S::zero();
+#pragma unroll 4
+            for (int p = 0; p < plen; ++p) {
+                const V_t lu = __ldg(V + (long long)__ldg(a.pa + pbeg + p) * a.lpad + sm);
+                const V_t xv = __ldcg(X + (long long)(__ldg(a.pb + pbeg + p) - a.n_val) * a.Q + q);
+                S::fma_acc(acc, lu, xv);
+            }
+            V_t* o = X + (long long)(__ldg(a.out + t) - a.n_val) * a.Q + q;
+            V_t v = S::sub(__ldcg(o), acc);
+            if (__ldg(a.kind + t) >= TK_MUL) v = S::mul(v, __ldg(V + (long long)__ldg(a.div + t) * a.lpad + sm));
+            *o = v;
+        }
+        if (l + 1 < a.nlevels) grid_barrier(a.barrier, gridDim.x, target);
+    }
+}
+
+// X[k][m*r+c] = b[m][perm[k]][c] (/ Rs[perm[k]][m])
+template <typename T>
+__global__ void lv_load_x(int L, int n, int r, const typename Sc<T>::V* __restrict__ b,
+                          long long b_stride, const int* __restrict__ perm, int scale,
+                          const double* __restrict__ Rs, long long lpad,
+                          const int* __restrict__ sysidx, typename Sc<T>::V* __restrict__ X) {
+    using S = Sc<T>;
+    const long long Q = (long long)L * r;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= Q * n) return;
+    const long long q = tid % Q;
+    const int k = static_cast<int>(tid / Q);
+    const int m = static_cast<int>(q / r), c = static_cast<int>(q % r);
+    const int src = perm[k];
+    typename S::V v = b[(long long)m * b_stride + (long long)src * r + c];
+    if (scale) v = S::rdiv(v, Rs[(long long)src * lpad + (sysidx ? sysidx[m] : m)]);
+    X[(long long)k * Q + q] = v;
+}
+
+template <typename T>
+__global__ void lv_store_x(int L, int n, int r, typename Sc<T>::V* __restrict__ x,
+                           const int* __restrict__ perm, int scale, const double* __restrict__ Rs,
+                           long long lpad, const int* __restrict__ sysidx,
+                           const typename Sc<T>::V* __restrict__ X) {
+    using S = Sc<T>;
+    const long long Q = (long long)L * r;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= Q * n) return;
+    const long long q = tid % Q;
+    const int k = static_cast<int>(tid / Q);
+    const int m = static_cast<int>(q / r), c = static_cast<int>(q % r);
+    const int dst = perm[k];
+    typename S::V v = X[(long long)k * Q + q];
+    if (scale) v = S::rdiv(v, Rs[(long long)dst * lpad + (sysidx ? sysidx[m] : m)]);
+    x[((long long)m * n + dst) * r + c] = v;
+}
+
+__global__ void lv_finish_status(int L, const int* __restrict__ bad,
+                                 const unsigned long long* __restrict__ growth2,
+                                 const int* __restrict__ pattern_bad, int32_t* status,
+                                 double* growth) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= L) return;
+    int st = bad[m] ? 1 : 0;
+    if (pattern_bad && *pattern_bad) st = -3;
+    if (status) status[m] = st;
+    if (growth) growth[m] = sqrt(__longlong_as_double((long long)growth2[m]));
+}
+
+template <typename T>
+static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::string& err) {
+    using V_t = typename Sc<T>::V;
+    auto chk = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess) {
+            err = std::string(what) + ": " + cudaGetErrorString(e);
+            return false;
+        }
+        return true;
+    };
+    const bool own_storage = (c.V == nullptr);
+    V_t* V = static_cast<V_t*>(c.V);
+    double* Rs = c.Rs;
+    long long lpad = c.lpad;
+    void *tmpV = nullptr, *tmpRs = nullptr, *tmpX = nullptr, *tmpAux = nullptr;
+    auto cleanup = [&]() {
+        // stream-ordered frees: the buffers stay valid for the work enqueued above
+        if (tmpV) cudaFreeAsync(tmpV, c.st);
+        if (tmpRs) cudaFreeAsync(tmpRs, c.st);
+        if (tmpX) cudaFreeAsync(tmpX, c.st);
+        if (tmpAux) cudaFreeAsync(tmpAux, c.st);
+    };
+    if (own_storage) {
+        lpad = (c.L + 31) / 32 * 32;
+        if (!chk(cudaMallocAsync(&tmpV, sizeof(V_t) * (size_t)c.n_val * lpad, c.st), "alloc V") ||
+            !chk(cudaMallocAsync(&tmpRs, sizeof(double) * (size_t)c.n * lpad, c.st), "alloc Rs")) {
+            cleanup();
+            return KLU_OUT_OF_MEMORY;
+        }
+        V = static_cast<V_t*>(tmpV);
+        Rs = static_cast<double*>(tmpRs);
+    }
+    // aux: barrier counters (2), bad[L], growth2[L]
+    const size_t aux_bytes = 64 + sizeof(int) * (size_t)c.L + sizeof(unsigned long long) * (size_t)c.L + 64;
+    if (!chk(cudaMallocAsync(&tmpAux, aux_bytes, c.st), "alloc aux") ||
+        !chk(cudaMemsetAsync(tmpAux, 0, aux_bytes, c.st), "memset aux")) {
+        cleanup();
+        return KLU_OUT_OF_MEMORY;
+    }
+    unsigned* barrier = static_cast<unsigned*>(tmpAux);
+    unsigned long long* growth2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(tmpAux) + 64);
+    int* bad = reinterpret_cast<int*>(growth2 + c.L);
+
+    int blocks_per_sm = 0;
+    const bool factor = (pf != nullptr);
+    if (factor) {
+        const long long tot = (long long)c.n_val * c.L;
+        const int zb = static_cast<int>(std::min<long long>((tot + 255) / 256, 148LL * 16));
+        lv_zero_slots<T><<<zb, 256, 0, c.st>>>(c.L, c.n_val, c.sysidx, V, lpad);
+        dim3 tb(32, 8), tg((c.nz + 31) / 32, (c.L + 31) / 32);
+        lv_scatter<T><<<tg, tb, 0, c.st>>>(c.L, c.nz, static_cast<const V_t*>(c.Ax), c.ax_stride,
+                                          c.coo_dst, c.sysidx, V, lpad);
+        const long long rt = (long long)c.n * c.L;
+        lv_rowscale<T><<<static_cast<unsigned>((rt + 255) / 256), 256, 0, c.st>>>(
+            c.L, c.n, c.rs_ptr, c.rs_slot, c.sysidx, V, Rs, lpad);
+        LvArgs a;
+        a.out = pf->d_out; a.div = pf->d_div; a.pbeg = pf->d_pbeg; a.plen = pf->d_plen;
+        a.kind = pf->d_kind; a.pa = pf->d_pa; a.pb = pf->d_pb; a.level_ptr = pf->d_level_ptr;
+        a.nlevels = pf->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = 1; a.lpad = lpad; a.Q = c.L;
+        a.V = V; a.X = nullptr; a.sysidx = c.sysidx; a.barrier = barrier; a.bad = bad; a.growth2 = growth2;
+        if (!chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, lv_factor<T>, 256, 0), "occupancy")) {
+            cleanup();
+            return KLU_OUT_OF_MEMORY;
+        }
+        const long long max_items = (long long)pf->max_level_tasks * ((c.L + 31) & ~31);
+        int grid = static_cast<int>(std::min<long long>((long long)blocks_per_sm * c.num_sms,
+                                                        std::max<long long>(1, (max_items + 255) / 256)));
+        void* args[] = {&a};
+        if (!chk(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lv_factor<T>), dim3(grid), dim3(256),
+                                             args, 0, c.st), "launch lv_factor")) {
+            cleanup();
+            return KLU_OUT_OF_MEMORY;
+        }
+        lv_finish_status<<<(c.L + 255) / 256, 256, 0, c.st>>>(c.L, bad, growth2, c.pattern_bad,
+                                                            c.status, c.growth);
+    }
+    if (ps) {
+        const bool tr = (c.mode == PM_FACTOR_TSOLVE || c.mode == PM_TSOLVE);
+        const long long Q = (long long)c.L * c.r;
+        if (!chk(cudaMallocAsync(&tmpX, sizeof(V_t) * (size_t)c.n * Q, c.st), "alloc X")) {
+            cleanup();
+            return KLU_OUT_OF_MEMORY;
+        }
+        V_t* X = static_cast<V_t*>(tmpX);
+        const long long tot = Q * c.n;
+        lv_load_x<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
+            c.L, c.n, c.r, static_cast<const V_t*>(c.b), c.b_stride, tr ? c.q : c.pnum, tr ? 0 : 1,
+            Rs, lpad, c.sysidx, X);
+        LvArgs a;
+        a.out = ps->d_out; a.div = ps->d_div; a.pbeg = ps->d_pbeg; a.plen = ps->d_plen;
+        a.kind = ps->d_kind; a.pa = ps->d_pa; a.pb = ps->d_pb; a.level_ptr = ps->d_level_ptr;
+        a.nlevels = ps->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = c.r; a.lpad = lpad; a.Q = Q;
+        a.V = V; a.X = X; a.sysidx = c.sysidx; a.barrier = barrier + 8; a.bad = bad; a.growth2 = growth2;
+        if (!chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, lv_solve<T>, 256, 0), "occupancy")) {
+            cleanup();
+            return KLU_OUT_OF_MEMORY;
+        }
+        const long long max_items = (long long)ps->max_level_tasks * ((Q + 31) & ~31LL);
+        int grid = static_cast<int>(std::min<long long>((long long)blocks_per_sm * c.num_sms,
+                                                        std::max<long long>(1, (max_items + 255) / 256)));
+        void* args[] = {&a};
+        if (!chk(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lv_solve<T>), dim3(grid), dim3(256),
+                                             args, 0, c.st), "launch lv_solve")) {
+            cleanup();
+            return KLU_OUT_OF_MEMORY;
+        }
+        lv_store_x<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
+            c.L, c.n, c.r, static_cast<V_t*>(c.x), tr ? c.pnum : c.q, tr ? 1 : 0, Rs, lpad, c.sysidx, X);
+    }
+    if (!chk(cudaGetLastError(), "level kernels")) {
+        cleanup();
+        return KLU_OUT_OF_MEMORY;
+    }
+    cleanup();
+    return 0;
+}
+
+static int level_run(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::string& err) {
+    return c.is_complex ? level_run_t<zc>(c, pf, ps, err) : level_run_t<double>(c, pf, ps, err);
+}
+
+// ---- dot_f64 / dot_c128: b[m,i,k] = sum_e Ax[m,e] * x[m,Aj[e],k] over Ai[e] = i ----
+template <typename T>
+__global__ void spmm_kernel(int L, int n, int r, int nz, const int* __restrict__ Ai,
+                            const int* __restrict__ Aj, const typename Sc<T>::V* __restrict__ Ax,
+                            const typename Sc<T>::V* __restrict__ x, double* __restrict__ b) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)L * nz * r;
+    if (tid >= total) return;
+    const int k = static_cast<int>(tid % r);
+    const long long t2 = tid / r;
+    const int e = static_cast<int>(t2 % nz);
+    const long long m = t2 / nz;
+    const int i = Ai[e], j = Aj[e];
+    if (i < 0 || i >= n || j < 0 || j >= n) return;
+    const typename Sc<T>::V p = Sc<T>::mul(Ax[m * nz + e], x[(m * n + j) * r + k]);
+    constexpr int W = sizeof(typename Sc<T>::V) / sizeof(double);
+    double* dst = b + ((m * n + i) * r + k) * W;
+    const double* pv = reinterpret_cast<const double*>(&p);
+#pragma unroll
+    for (int w = 0; w < W; ++w) atomicAdd(dst + w, pv[w]);
+}
+
+static int coo_spmm(int cx, int L, int n, int r, int nz, const int* Ai, const int* Aj,
+                    const double* Ax, const double* x, double* b, cudaStream_t st, std::string& err) {
+    const size_t bytes = sizeof(double) * (cx ? 2 : 1) * (size_t)L * n * r;
+    if (cudaMemsetAsync(b, 0, bytes, st) != cudaSuccess) {
+        err = "dot: memset failed";
+        return KLU_INVALID;
+    }
+    const long long total = (long long)L * nz * r;
+    if (total == 0) return 0;
+    const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+    if (cx)
+        spmm_kernel<zc><<<grid, 256, 0, st>>>(L, n, r, nz, Ai, Aj, reinterpret_cast<const double2*>(Ax),
+                                              reinterpret_cast<const double2*>(x), b);
+    else
+        spmm_kernel<double><<<grid, 256, 0, st>>>(L, n, r, nz, Ai, Aj, Ax, x, b);
+    if (cudaGetLastError() != cudaSuccess) {
+        err = "dot: launch failed";
+        return KLU_INVALID;
+    }
+    return 0;
+}
+
+}  // namespace kb

@@ -1,0 +1,896 @@
+// klujax_cuda.cu — C-ABI (include/klujax_cuda.h) and host-side handle objects of
+// the B200 twin of klujax's numeric hot path.  Each extern "C" entry point stands
+// where one XLA-FFI handler of /root/reference/klujax.cpp stands; the shape
+// parsing those handlers do (klujax.cpp:17-84, :1011-1064) is the caller's job
+// (klujax_b200/api.py mirrors klujax.py for it).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/klujax_cuda.h"
+#include "plan.hpp"
+#include "symbolic.hpp"
+#include "kernels_small.cuh"
+#include "kernels_level.cuh"
+
+namespace kb {
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_OK(call)                                                                    \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(KLU_OUT_OF_MEMORY, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t alloc(size_t nbytes) {
+        release();
+        bytes = nbytes;
+        return cudaMalloc(&p, nbytes ? nbytes : 16);
+    }
+    template <typename U>
+    cudaError_t upload(const std::vector<U>& v) {
+        cudaError_t e = alloc(v.size() * sizeof(U));
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(p, v.data(), v.size() * sizeof(U), cudaMemcpyHostToDevice);
+    }
+    template <typename U>
+    U* as() const {
+        return static_cast<U*>(p);
+    }
+};
+
+struct SmallProg {
+    DevBuf ctrl, stream;
+    int nbatch = 0, n_slots = 0, zero_slot = 0, nlevels = 0;
+    int64_t n_mac = 0;
+};
+
+// Everything that depends on the pivot sequence (one per value type).
+struct Seeded {
+    bool ok = false;
+    PivotPlan piv;
+    SlotLayout lay;
+    int regime = 0;  // 0 = shared-memory warp-per-system, 1 = level-scheduled global
+    DevBuf d_colptr, d_srow, d_sslot, d_rs_ptr, d_rs_slot, d_pnum, d_q;
+    std::map<std::pair<int, int>, std::unique_ptr<SmallProg>> small;
+    std::map<std::pair<int, int>, std::unique_ptr<LevelProg>> level;
+    int64_t info_levels = 0, info_mac = 0;
+};
+
+struct Symbolic {
+    CscPattern A;
+    Ordering ord;
+    std::vector<int> Ai, Aj;  // COO of the analyze call
+    Seeded seeded[2];
+    DevBuf d_coo_dst, d_bad;
+    std::mutex mu;
+};
+
+struct NumericBatch {
+    uint32_t id = 0;
+    Symbolic* sym = nullptr;
+    int is_complex = 0, regime = 0, L = 0, live = 0;
+    int64_t lpad = 0;  // level regime: padded batch stride
+    DevBuf V, Rs;
+    std::vector<uint8_t> freed;
+};
+
+static std::mutex g_reg_mu;
+static std::unordered_map<uint32_t, NumericBatch*> g_batches;
+static uint32_t g_next_batch = 1;
+static int g_num_sms = 0;
+
+static int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+static inline Symbolic* sym_of(uint64_t h) { return reinterpret_cast<Symbolic*>(static_cast<uintptr_t>(h)); }
+
+// ---------------------------------------------------------------------------
+// seeding: one pivoting factorization on the host fixes pivots and patterns
+// ---------------------------------------------------------------------------
+static constexpr size_t kMaxDynSmem = 232448;  // 227 KB per CTA on sm_100
+
+template <typename T>
+static int seed_from_csc_values(Symbolic* S, int cx, const T* csc_values) {
+    Seeded& sd = S->seeded[cx];
+    if (!seed_factor<T>(S->A, S->ord, csc_values, sd.piv)) {
+        const int st = sd.piv.status;
+        return fail(st ? st : KLU_SINGULAR,
+                    st == KLU_INVALID ? "duplicate entries in the pattern (coalesce first)"
+                                      : "seed system is singular: cannot fix a pivot sequence");
+    }
+    build_layout(S->A, S->ord, sd.piv, sd.lay);
+    // regime: does factor+solve with one right-hand side fit in shared memory?
+    TaskProgram tp;
+    PackedProgram pp;
+    const size_t vsz = cx ? 16 : 8;
+    sd.regime = 1;
+    if (static_cast<size_t>(sd.lay.n_val + sd.lay.n + 1) * vsz + sd.lay.n * 8ull <= kMaxDynSmem &&
+        sd.lay.n_val + sd.lay.n + 1 <= 16383) {
+        build_program(S->ord, sd.piv, sd.lay, PM_FACTOR_SOLVE, 1, tp);
+        if (pack_program(sd.lay, tp, pp)) sd.regime = 0;
+        sd.info_levels = tp.nlevels;
+    }
+    if (const char* force = std::getenv("KLUJAX_CUDA_FORCE_REGIME")) sd.regime = std::atoi(force) ? 1 : 0;
+    {
+        TaskProgram tf;
+        if (sd.regime == 0 || sd.lay.n_lu < 4000000) {
+            build_program(S->ord, sd.piv, sd.lay, PM_FACTOR, 0, tf);
+            sd.info_mac = tf.n_mac;
+            if (sd.regime == 1) sd.info_levels = tf.nlevels;
+        }
+    }
+    sd.ok = true;
+    return 0;
+}
+
+static int upload_seeded(Symbolic* S, int cx) {
+    Seeded& sd = S->seeded[cx];
+    if (sd.d_colptr.p) return 0;
+    CUDA_OK(sd.d_colptr.upload(sd.lay.sorted_colptr));
+    CUDA_OK(sd.d_srow.upload(sd.lay.sorted_row));
+    CUDA_OK(sd.d_sslot.upload(sd.lay.sorted_slot));
+    CUDA_OK(sd.d_rs_ptr.upload(sd.lay.rs_ptr));
+    CUDA_OK(sd.d_rs_slot.upload(sd.lay.rs_slot));
+    CUDA_OK(sd.d_pnum.upload(sd.piv.Pnum));
+    CUDA_OK(sd.d_q.upload(S->ord.Q));
+    if (!S->d_coo_dst.p) {
+        CUDA_OK(S->d_coo_dst.alloc(sizeof(int) * (S->A.rowidx.size() + 1)));
+        CUDA_OK(S->d_bad.alloc(sizeof(int)));
+    }
+    return 0;
+}
+
+// values of one system given in some COO order -> the analysed CSC order
+template <typename T>
+static int seed_from_coo(Symbolic* S, int cx, int nz, const int* Ai, const int* Aj, const T* Ax0) {
+    const CscPattern& A = S->A;
+    if (nz != static_cast<int>(A.rowidx.size()))
+        return fail(KLU_INVALID, "n_nz differs from the analysed pattern");
+    // (col,row) -> csc position through a per-column sorted view
+    std::vector<int> order(nz);
+    for (int j = 0; j < A.n; ++j) {
+        for (int p = A.colptr[j]; p < A.colptr[j + 1]; ++p) order[p] = p;
+        std::sort(order.begin() + A.colptr[j], order.begin() + A.colptr[j + 1],
+                  [&](int x, int y) { return A.rowidx[x] < A.rowidx[y]; });
+    }
+    std::vector<T> csc(nz, T(0));
+    for (int e = 0; e < nz; ++e) {
+        const int i = Ai[e], j = Aj[e];
+        if (i < 0 || i >= A.n || j < 0 || j >= A.n) return fail(KLU_INVALID, "index out of range");
+        auto b = order.begin() + A.colptr[j], en = order.begin() + A.colptr[j + 1];
+        auto it = std::lower_bound(b, en, i, [&](int p, int row) { return A.rowidx[p] < row; });
+        if (it == en || A.rowidx[*it] != i)
+            return fail(KLU_INVALID, "entry outside the analysed sparsity pattern");
+        csc[*it] = Ax0[e];
+    }
+    return seed_from_csc_values<T>(S, cx, csc.data());
+}
+
+static int ensure_seeded_dev(Symbolic* S, int cx, int nz, const int32_t* Ai_dev,
+                             const int32_t* Aj_dev, const void* Ax_dev, cudaStream_t st) {
+    Seeded& sd = S->seeded[cx];
+    if (!sd.ok) {
+        if (nz != static_cast<int>(S->A.rowidx.size()))
+            return fail(KLU_INVALID, "n_nz differs from the analysed pattern");
+        std::vector<int> Ai(nz), Aj(nz);
+        std::vector<double> Ax(static_cast<size_t>(nz) * (cx ? 2 : 1));
+        CUDA_OK(cudaMemcpyAsync(Ai.data(), Ai_dev, sizeof(int) * nz, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(Aj.data(), Aj_dev, sizeof(int) * nz, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(Ax.data(), Ax_dev, sizeof(double) * Ax.size(), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        int rc = cx ? seed_from_coo<std::complex<double>>(
+                          S, 1, nz, Ai.data(), Aj.data(),
+                          reinterpret_cast<const std::complex<double>*>(Ax.data()))
+                    : seed_from_coo<double>(S, 0, nz, Ai.data(), Aj.data(), Ax.data());
+        if (rc) return rc;
+    }
+    return upload_seeded(S, cx);
+}
+
+// ---------------------------------------------------------------------------
+// program caches
+// ---------------------------------------------------------------------------
+static int get_small_prog(Symbolic* S, int cx, int mode, int rc, SmallProg** out) {
+    Seeded& sd = S->seeded[cx];
+    auto key = std::make_pair(mode, rc);
+    auto it = sd.small.find(key);
+    if (it == sd.small.end()) {
+        TaskProgram tp;
+        PackedProgram pp;
+        build_program(S->ord, sd.piv, sd.lay, mode, rc, tp);
+        if (!pack_program(sd.lay, tp, pp)) return fail(KLU_TOO_LARGE, "program does not fit the shared-memory regime");
+        auto sp = std::make_unique<SmallProg>();
+        CUDA_OK(sp->ctrl.upload(pp.ctrl));
+        CUDA_OK(sp->stream.upload(pp.stream));
+        sp->nbatch = pp.nbatch;
+        sp->n_slots = pp.n_slots;
+        sp->zero_slot = pp.zero_slot;
+        sp->nlevels = tp.nlevels;
+        sp->n_mac = tp.n_mac;
+        it = sd.small.emplace(key, std::move(sp)).first;
+    }
+    *out = it->second.get();
+    return 0;
+}
+
+static int get_level_prog(Symbolic* S, int cx, int mode, LevelProg** out) {
+    Seeded& sd = S->seeded[cx];
+    auto key = std::make_pair(mode, 1);
+    auto it = sd.level.find(key);
+    if (it == sd.level.end()) {
+        TaskProgram tp;
+        build_program(S->ord, sd.piv, sd.lay, mode, 1, tp);
+        auto lp = std::make_unique<LevelProg>();
+        std::string err;
+        if (!lp->upload(sd.lay, tp, err)) return fail(KLU_OUT_OF_MEMORY, err);
+        it = sd.level.emplace(key, std::move(lp)).first;
+    }
+    *out = it->second.get();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// the one numeric driver behind every entry point
+// ---------------------------------------------------------------------------
+struct Op {
+    int mode = PM_FACTOR_SOLVE;
+    int L = 0, r = 0, nz = 0;
+    const int32_t *Ai = nullptr, *Aj = nullptr;
+    const void* Ax = nullptr;
+    long long ax_stride = 0;
+    const void* b = nullptr;
+    long long b_stride = 0;
+    void* x = nullptr;
+    NumericBatch* batch = nullptr;  // store (factor modes) or load (solve modes)
+    bool store_numeric = false;
+    const int* sysidx_dev = nullptr;
+    int32_t* status = nullptr;
+    double* growth = nullptr;
+    cudaStream_t st = nullptr;
+};
+
+template <typename T>
+static int launch_small(Symbolic* S, int cx, const Op& op) {
+    Seeded& sd = S->seeded[cx];
+    const int n = sd.lay.n;
+    const bool factor = op.mode <= PM_FACTOR_TSOLVE;
+    const bool solve = op.mode != PM_FACTOR;
+    const bool transpose = (op.mode == PM_FACTOR_TSOLVE || op.mode == PM_TSOLVE);
+    const size_t vsz = sizeof(typename Sc<T>::V);
+    int rc = 0;
+    SmallProg *p0 = nullptr, *p1 = nullptr;
+    if (solve) {
+        // widest right-hand-side chunk that still fits the slot fields / shared memory
+        for (rc = std::min(op.r, 4); rc >= 1; --rc) {
+            const size_t slots = static_cast<size_t>(sd.lay.n_val) + static_cast<size_t>(n) * rc + 1;
+            if (slots <= 16383 && slots * vsz + n * 8ull <= kMaxDynSmem) break;
+        }
+        if (rc < 1) return fail(KLU_TOO_LARGE, "system does not fit the shared-memory regime");
+    }
+    int e = get_small_prog(S, cx, op.mode, rc, &p0);
+    if (e) return e;
+    if (solve && op.r > rc) {
+        e = get_small_prog(S, cx, transpose ? PM_TSOLVE : PM_SOLVE, rc, &p1);
+        if (e) return e;
+    }
+    SmallArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.ctrl[0] = p0->ctrl.as<uint32_t>();
+    a.stream[0] = p0->stream.as<uint32_t>();
+    a.nbatch[0] = p0->nbatch;
+    if (p1) {
+        a.ctrl[1] = p1->ctrl.as<uint32_t>();
+        a.stream[1] = p1->stream.as<uint32_t>();
+        a.nbatch[1] = p1->nbatch;
+    }
+    a.n = n;
+    a.n_val = sd.lay.n_val;
+    a.n_slots = p0->n_slots;
+    a.zero_slot = p0->zero_slot;
+    a.rc = rc;
+    a.nz = op.nz;
+    a.flags = (factor ? SF_FACTOR : SF_LOAD_NUMERIC) | (solve ? SF_SOLVE : 0) |
+              (op.store_numeric ? SF_STORE_NUMERIC : 0) |
+              (solve ? (transpose ? SF_SCALE_OUT : SF_SCALE_IN) : 0);
+    a.coo_dst = S->d_coo_dst.as<int>();
+    a.pattern_bad = S->d_bad.as<int>();
+    a.rs_ptr = sd.d_rs_ptr.as<int>();
+    a.rs_slot = sd.d_rs_slot.as<int>();
+    a.in_perm = transpose ? sd.d_q.as<int>() : sd.d_pnum.as<int>();
+    a.out_perm = transpose ? sd.d_pnum.as<int>() : sd.d_q.as<int>();
+    a.Ax = op.Ax;
+    a.ax_stride = op.ax_stride;
+    a.b = op.b;
+    a.b_stride = op.b_stride;
+    a.x = op.x;
+    a.r = op.r;
+    if (op.batch) {
+        a.Vstore = op.batch->V.p;
+        a.Rsstore = op.batch->Rs.as<double>();
+    }
+    a.sysidx = op.sysidx_dev;
+    a.status = op.status;
+    a.growth = op.growth;
+    a.L = op.L;
+    const size_t smem = static_cast<size_t>(a.n_slots) * vsz + n * 8ull;
+    auto kern = small_kernel<T>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int occ = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
+    if (occ < 1) return fail(KLU_TOO_LARGE, "shared-memory regime: zero occupancy");
+    const int grid = static_cast<int>(std::min<long long>(op.L, static_cast<long long>(occ) * num_sms()));
+    kern<<<grid, 32, smem, op.st>>>(a);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int run_numeric(Symbolic* S, int cx, const Op& op) {
+    std::lock_guard<std::mutex> lock(S->mu);
+    Seeded& sd = S->seeded[cx];
+    const bool factor = op.mode <= PM_FACTOR_TSOLVE;
+    if (op.L <= 0) return 0;
+    if (factor) {
+        int e = ensure_seeded_dev(S, cx, op.nz, op.Ai, op.Aj, op.Ax, op.st);
+        if (e) return e;
+        CUDA_OK(cudaMemsetAsync(S->d_bad.p, 0, sizeof(int), op.st));
+        const int nz = op.nz;
+        coo_map_kernel<<<(nz + 255) / 256, 256, 0, op.st>>>(
+            nz, sd.lay.n, op.Ai, op.Aj, sd.d_colptr.as<int>(), sd.d_srow.as<int>(),
+            sd.d_sslot.as<int>(), S->d_coo_dst.as<int>(), S->d_bad.as<int>());
+        CUDA_OK(cudaGetLastError());
+    } else if (!sd.ok) {
+        return fail(KLU_INVALID, "numeric handle without a factorization");
+    }
+    if (sd.regime == 0) return cx ? launch_small<zc>(S, 1, op) : launch_small<double>(S, 0, op);
+    // level-scheduled regime
+    LevelCall lc;
+    lc.mode = op.mode;
+    lc.L = op.L;
+    lc.r = op.r;
+    lc.nz = op.nz;
+    lc.Ax = op.Ax;
+    lc.ax_stride = op.ax_stride;
+    lc.b = op.b;
+    lc.b_stride = op.b_stride;
+    lc.x = op.x;
+    lc.coo_dst = S->d_coo_dst.as<int>();
+    lc.pattern_bad = S->d_bad.as<int>();
+    lc.rs_ptr = sd.d_rs_ptr.as<int>();
+    lc.rs_slot = sd.d_rs_slot.as<int>();
+    lc.pnum = sd.d_pnum.as<int>();
+    lc.q = sd.d_q.as<int>();
+    lc.sysidx = op.sysidx_dev;
+    lc.status = op.status;
+    lc.growth = op.growth;
+    lc.st = op.st;
+    lc.n = sd.lay.n;
+    lc.n_val = sd.lay.n_val;
+    lc.is_complex = cx;
+    lc.num_sms = num_sms();
+    if (op.batch) {
+        lc.V = op.batch->V.p;
+        lc.Rs = op.batch->Rs.as<double>();
+        lc.lpad = op.batch->lpad;
+        lc.Lstore = op.batch->L;
+    }
+    LevelProg *pf = nullptr, *ps = nullptr;
+    if (factor) {
+        int e = get_level_prog(S, cx, PM_FACTOR, &pf);
+        if (e) return e;
+    }
+    if (op.mode != PM_FACTOR) {
+        const bool tr = (op.mode == PM_FACTOR_TSOLVE || op.mode == PM_TSOLVE);
+        int e = get_level_prog(S, cx, tr ? PM_TSOLVE : PM_SOLVE, &ps);
+        if (e) return e;
+    }
+    std::string err;
+    int rc = level_run(lc, pf, ps, err);
+    if (rc) return fail(rc, err);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// numeric batches (device-resident counterpart of klu_numeric* arrays)
+// ---------------------------------------------------------------------------
+static int new_batch(Symbolic* S, int cx, int L, NumericBatch** out) {
+    Seeded& sd = S->seeded[cx];
+    auto nb = std::make_unique<NumericBatch>();
+    nb->sym = S;
+    nb->is_complex = cx;
+    nb->regime = sd.regime;
+    nb->L = L;
+    nb->live = L;
+    nb->freed.assign(L, 0);
+    const size_t vsz = cx ? 16 : 8;
+    nb->lpad = (L + 31) / 32 * 32;
+    const size_t nsys = sd.regime == 0 ? static_cast<size_t>(L) : static_cast<size_t>(nb->lpad);
+    CUDA_OK(nb->V.alloc(nsys * sd.lay.n_val * vsz));
+    CUDA_OK(nb->Rs.alloc(nsys * sd.lay.n * sizeof(double)));
+    {
+        std::lock_guard<std::mutex> g(g_reg_mu);
+        nb->id = g_next_batch++;
+        g_batches[nb->id] = nb.get();
+    }
+    *out = nb.release();
+    return 0;
+}
+
+// resolves a host array of handles to (batch, per-system element index)
+static int resolve_numeric(int n, const uint64_t* h, NumericBatch** out, std::vector<int>& idx,
+                           bool& identity) {
+    if (n <= 0) return fail(KLU_INVALID, "empty numeric handle array");
+    idx.resize(n);
+    NumericBatch* nb = nullptr;
+    identity = true;
+    std::lock_guard<std::mutex> g(g_reg_mu);
+    for (int m = 0; m < n; ++m) {
+        if (h[m] == 0) return fail(KLU_INVALID, "numeric pointer is null");
+        const uint32_t id = static_cast<uint32_t>(h[m] >> 32);
+        const int el = static_cast<int>(h[m] & 0xffffffffu) - 1;
+        auto it = g_batches.find(id);
+        if (it == g_batches.end()) return fail(KLU_INVALID, "stale numeric handle");
+        if (nb && it->second != nb)
+            return fail(KLU_INVALID, "numeric handles of different factor calls cannot be mixed");
+        nb = it->second;
+        if (el < 0 || el >= nb->L || nb->freed[el]) return fail(KLU_INVALID, "stale numeric handle");
+        idx[m] = el;
+        if (el != m) identity = false;
+    }
+    if (n != nb->L) identity = identity && false;
+    *out = nb;
+    return 0;
+}
+
+template <typename T>
+static int upload_idx(const std::vector<int>& idx, int L, DevBuf& buf, cudaStream_t st) {
+    // broadcast a single element to L systems, or use the list as it is
+    std::vector<int> full(L);
+    for (int m = 0; m < L; ++m) full[m] = idx.size() == 1 ? idx[0] : idx[m];
+    cudaError_t e = buf.alloc(sizeof(int) * L);
+    if (e != cudaSuccess) return fail(KLU_OUT_OF_MEMORY, cudaGetErrorString(e));
+    e = cudaMemcpyAsync(buf.p, full.data(), sizeof(int) * L, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(KLU_OUT_OF_MEMORY, cudaGetErrorString(e));
+    e = cudaStreamSynchronize(st);  // `full` dies with this scope
+    if (e != cudaSuccess) return fail(KLU_OUT_OF_MEMORY, cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace kb
+
+using namespace kb;
+
+// ===========================================================================
+// extern "C"
+// ===========================================================================
+extern "C" {
+
+int klujax_cuda_abi_version(void) { return KLUJAX_CUDA_ABI_VERSION; }
+const char* klujax_cuda_last_error(void) { return g_err.c_str(); }
+
+int klujax_cuda_analyze(int n_col, int n_nz, const int32_t* Ai, const int32_t* Aj, uint64_t* out) {
+    if (out) *out = 0;
+    if (!out || n_col <= 0 || n_nz < 0 || (n_nz > 0 && (!Ai || !Aj)))
+        return fail(KLU_INVALID, "analyze: bad arguments");
+    for (int e = 0; e < n_nz; ++e) {
+        if (Ai[e] < 0 || Ai[e] >= n_col) return fail(KLU_INVALID, "Ai index out of bounds.");
+        if (Aj[e] < 0 || Aj[e] >= n_col) return fail(KLU_INVALID, "Aj index out of bounds.");
+    }
+    auto S = std::make_unique<Symbolic>();
+    S->A = coo_to_csc(n_col, n_nz, Ai, Aj);
+    S->Ai.assign(Ai, Ai + n_nz);
+    S->Aj.assign(Aj, Aj + n_nz);
+    if (!analyze_pattern(S->A, S->ord)) return fail(KLU_INVALID, "klu_analyze failed.");
+    *out = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(S.release()));
+    return 0;
+}
+
+int klujax_cuda_free_symbolic(uint64_t symbolic, int32_t* freed) {
+    if (symbolic == 0) {
+        if (freed) *freed = 0;
+        return 0;
+    }
+    delete sym_of(symbolic);
+    if (freed) *freed = 1;
+    return 0;
+}
+
+int klujax_cuda_seed_host(uint64_t symbolic, int is_complex, const double* Ax_host) {
+    Symbolic* S = sym_of(symbolic);
+    if (!S || !Ax_host) return fail(KLU_INVALID, "seed_host: null argument");
+    std::lock_guard<std::mutex> lock(S->mu);
+    const int nz = static_cast<int>(S->Ai.size());
+    if (is_complex)
+        return seed_from_coo<std::complex<double>>(S, 1, nz, S->Ai.data(), S->Aj.data(),
+                                                   reinterpret_cast<const std::complex<double>*>(Ax_host));
+    return seed_from_coo<double>(S, 0, nz, S->Ai.data(), S->Aj.data(), Ax_host);
+}
+
+int klujax_cuda_symbolic_info(uint64_t symbolic, int is_complex, int64_t* o) {
+    Symbolic* S = sym_of(symbolic);
+    if (!S || !o) return fail(KLU_INVALID, "symbolic_info: null argument");
+    const Seeded& sd = S->seeded[is_complex ? 1 : 0];
+    o[0] = S->ord.n;
+    o[1] = S->ord.nblocks;
+    o[2] = S->ord.maxblock;
+    o[3] = S->ord.nzoff;
+    o[4] = S->ord.structural_rank;
+    o[5] = sd.ok ? sd.lay.nnz_l : -1;
+    o[6] = sd.ok ? sd.lay.nnz_u : -1;
+    o[7] = sd.ok ? 1 : 0;
+    o[8] = sd.ok ? sd.regime : -1;
+    o[9] = sd.ok ? sd.info_levels : -1;
+    o[10] = sd.ok ? sd.info_mac : -1;
+    o[11] = sd.ok ? sd.piv.noffdiag : -1;
+    return 0;
+}
+
+int klujax_cuda_symbolic_perm(uint64_t symbolic, int32_t* P, int32_t* Q, int32_t* R) {
+    Symbolic* S = sym_of(symbolic);
+    if (!S) return fail(KLU_INVALID, "symbolic_perm: null handle");
+    if (P) std::copy(S->ord.P.begin(), S->ord.P.end(), P);
+    if (Q) std::copy(S->ord.Q.begin(), S->ord.Q.end(), Q);
+    if (R) std::copy(S->ord.R.begin(), S->ord.R.begin() + S->ord.nblocks + 1, R);
+    return 0;
+}
+
+int klujax_cuda_symbolic_pattern(uint64_t symbolic, int is_complex, int32_t* Pnum, int32_t* Lp,
+                                 int32_t* Li, int32_t* Up, int32_t* Ui) {
+    Symbolic* S = sym_of(symbolic);
+    if (!S) return fail(KLU_INVALID, "symbolic_pattern: null handle");
+    const Seeded& sd = S->seeded[is_complex ? 1 : 0];
+    if (!sd.ok) return fail(KLU_INVALID, "symbolic_pattern: not seeded");
+    const int n = sd.lay.n;
+    if (Pnum) std::copy(sd.piv.Pnum.begin(), sd.piv.Pnum.end(), Pnum);
+    std::vector<int> k1(n);
+    for (int b = 0; b < S->ord.nblocks; ++b)
+        for (int k = S->ord.R[b]; k < S->ord.R[b + 1]; ++k) k1[k] = S->ord.R[b];
+    int lp = 0, up = 0;
+    for (int k = 0; k < n; ++k) {
+        if (Up) Up[k] = up;
+        if (Lp) Lp[k] = lp;
+        for (int s = sd.lay.col_begin[k]; s < sd.lay.diag_slot[k]; ++s, ++up)
+            if (Ui) Ui[up] = sd.lay.slot_row[s] - k1[k];
+        for (int s = sd.lay.diag_slot[k] + 1; s < sd.lay.col_begin[k + 1]; ++s, ++lp)
+            if (Li) Li[lp] = sd.lay.slot_row[s] - k1[k];
+    }
+    if (Up) Up[n] = up;
+    if (Lp) Lp[n] = lp;
+    return 0;
+}
+
+// ---- fused factor + (t)solve ------------------------------------------------
+static int do_solve_with_symbol(int cx, int transpose, uint64_t symbolic, int n_lhs, int n_col,
+                                int n_rhs, int n_nz, const int32_t* Ai, const int32_t* Aj,
+                                const double* Ax, const double* b, double* x, int32_t* status,
+                                double* growth, void* stream) {
+    Symbolic* S = sym_of(symbolic);
+    if (!S) return fail(KLU_INVALID, "symbolic pointer is null");
+    if (n_col != S->ord.n) return fail(KLU_INVALID, "n_col differs from the analysed matrix");
+    if (n_lhs <= 0 || n_rhs <= 0) return 0;
+    Op op;
+    op.mode = transpose ? PM_FACTOR_TSOLVE : PM_FACTOR_SOLVE;
+    op.L = n_lhs;
+    op.r = n_rhs;
+    op.nz = n_nz;
+    op.Ai = Ai;
+    op.Aj = Aj;
+    op.Ax = Ax;
+    op.ax_stride = n_nz;
+    op.b = b;
+    op.b_stride = static_cast<long long>(n_col) * n_rhs;
+    op.x = x;
+    op.status = status;
+    op.growth = growth;
+    op.st = static_cast<cudaStream_t>(stream);
+    return run_numeric(S, cx, op);
+}
+
+#define DEF_SWS(name, cx, tr)                                                                       \
+    int name(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai,       \
+             const int32_t* Aj, const double* Ax, const double* b, double* x, int32_t* status,      \
+             double* growth, void* stream) {                                                        \
+        return do_solve_with_symbol(cx, tr, symbolic, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, x,  \
+                                    status, growth, stream);                                        \
+    }
+DEF_SWS(klujax_cuda_solve_with_symbol_f64, 0, 0)
+DEF_SWS(klujax_cuda_solve_with_symbol_c128, 1, 0)
+DEF_SWS(klujax_cuda_tsolve_with_symbol_f64, 0, 1)
+DEF_SWS(klujax_cuda_tsolve_with_symbol_c128, 1, 1)
+
+static int do_solve(int cx, int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai_host,
+                    const int32_t* Aj_host, const double* Ax, const double* b, double* x,
+                    int32_t* status, double* growth, void* stream) {
+    uint64_t sym = 0;
+    int rc = klujax_cuda_analyze(n_col, n_nz, Ai_host, Aj_host, &sym);
+    if (rc) return rc;
+    DevBuf dAi, dAj;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = dAi.alloc(sizeof(int) * (n_nz + 1));
+    if (e == cudaSuccess) e = dAj.alloc(sizeof(int) * (n_nz + 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dAi.p, Ai_host, sizeof(int) * n_nz, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dAj.p, Aj_host, sizeof(int) * n_nz, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+        klujax_cuda_free_symbolic(sym, nullptr);
+        return fail(KLU_OUT_OF_MEMORY, cudaGetErrorString(e));
+    }
+    rc = do_solve_with_symbol(cx, 0, sym, n_lhs, n_col, n_rhs, n_nz, dAi.as<int32_t>(),
+                              dAj.as<int32_t>(), Ax, b, x, status, growth, stream);
+    cudaStreamSynchronize(st);  // the symbolic object dies with this call, like klujax.cpp:336
+    klujax_cuda_free_symbolic(sym, nullptr);
+    return rc;
+}
+int klujax_cuda_solve_f64(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai,
+                          const int32_t* Aj, const double* Ax, const double* b, double* x,
+                          int32_t* status, double* growth, void* stream) {
+    return do_solve(0, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, x, status, growth, stream);
+}
+int klujax_cuda_solve_c128(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai,
+                           const int32_t* Aj, const double* Ax, const double* b, double* x,
+                           int32_t* status, double* growth, void* stream) {
+    return do_solve(1, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, x, status, growth, stream);
+}
+
+// ---- factor / refactor / refactor_and_solve ---------------------------------
+static int do_factor(int cx, uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai,
+                     const int32_t* Aj, const double* Ax, uint64_t* numeric_out, int32_t* status,
+                     double* growth, void* stream) {
+    Symbolic* S = sym_of(symbolic);
+    if (!S) return fail(KLU_INVALID, "symbolic pointer is null");
+    if (n_lhs <= 0 || !numeric_out) return fail(KLU_INVALID, "factor: empty batch");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        std::lock_guard<std::mutex> lock(S->mu);
+        int e = ensure_seeded_dev(S, cx, n_nz, Ai, Aj, Ax, st);
+        if (e) return e;
+    }
+    NumericBatch* nb = nullptr;
+    int e = new_batch(S, cx, n_lhs, &nb);
+    if (e) return e;
+    Op op;
+    op.mode = PM_FACTOR;
+    op.L = n_lhs;
+    op.nz = n_nz;
+    op.Ai = Ai;
+    op.Aj = Aj;
+    op.Ax = Ax;
+    op.ax_stride = n_nz;
+    op.batch = nb;
+    op.store_numeric = true;
+    op.status = status;
+    op.growth = growth;
+    op.st = st;
+    e = run_numeric(S, cx, op);
+    if (e) {
+        std::lock_guard<std::mutex> g(g_reg_mu);
+        g_batches.erase(nb->id);
+        delete nb;
+        return e;
+    }
+    for (int m = 0; m < n_lhs; ++m)
+        numeric_out[m] = (static_cast<uint64_t>(nb->id) << 32) | static_cast<uint64_t>(m + 1);
+    return 0;
+}
+int klujax_cuda_factor_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai,
+                           const int32_t* Aj, const double* Ax, uint64_t* numeric_out,
+                           int32_t* status, double* growth, void* stream) {
+    return do_factor(0, symbolic, n_lhs, n_nz, Ai, Aj, Ax, numeric_out, status, growth, stream);
+}
+int klujax_cuda_factor_c128(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai,
+                            const int32_t* Aj, const double* Ax, uint64_t* numeric_out,
+                            int32_t* status, double* growth, void* stream) {
+    return do_factor(1, symbolic, n_lhs, n_nz, Ai, Aj, Ax, numeric_out, status, growth, stream);
+}
+
+static int do_refactor(int cx, int with_solve, uint64_t symbolic, int n_lhs, int n_col, int n_rhs,
+                       int n_nz, const int32_t* Ai, const int32_t* Aj, const double* Ax,
+                       const double* b, const uint64_t* numeric_in, double* x,
+                       uint64_t* numeric_out, int32_t* status, double* growth, void* stream) {
+    Symbolic* S = sym_of(symbolic);
+    if (!S) return fail(KLU_INVALID, "symbolic pointer is null");
+    if (!numeric_in) return fail(KLU_INVALID, "numeric pointer is null");
+    NumericBatch* nb = nullptr;
+    std::vector<int> idx;
+    bool identity = false;
+    int e = resolve_numeric(n_lhs, numeric_in, &nb, idx, identity);
+    if (e) return e;
+    if (nb->sym != S || nb->is_complex != cx)
+        return fail(KLU_INVALID, "numeric handle belongs to another symbolic handle / dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DevBuf didx;
+    if (!identity) {
+        e = upload_idx<int>(idx, n_lhs, didx, st);
+        if (e) return e;
+    }
+    Op op;
+    op.mode = with_solve ? PM_FACTOR_SOLVE : PM_FACTOR;
+    op.L = n_lhs;
+    op.r = with_solve ? n_rhs : 0;
+    op.nz = n_nz;
+    op.Ai = Ai;
+    op.Aj = Aj;
+    op.Ax = Ax;
+    op.ax_stride = n_nz;
+    op.b = b;
+    op.b_stride = static_cast<long long>(n_col) * n_rhs;
+    op.x = x;
+    op.batch = nb;
+    op.store_numeric = true;
+    op.sysidx_dev = identity ? nullptr : didx.as<int>();
+    op.status = status;
+    op.growth = growth;
+    op.st = st;
+    e = run_numeric(S, cx, op);
+    if (!identity) cudaStreamSynchronize(st);  // didx is released on return
+    if (e) return e;
+    if (numeric_out)
+        for (int m = 0; m < n_lhs; ++m) numeric_out[m] = numeric_in[m];  // klujax.cpp:785-786
+    return 0;
+}
+int klujax_cuda_refactor_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai,
+                             const int32_t* Aj, const double* Ax, const uint64_t* nin,
+                             uint64_t* nout, int32_t* status, double* growth, void* stream) {
+    return do_refactor(0, 0, symbolic, n_lhs, 0, 0, n_nz, Ai, Aj, Ax, nullptr, nin, nullptr, nout,
+                       status, growth, stream);
+}
+int klujax_cuda_refactor_c128(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai,
+                              const int32_t* Aj, const double* Ax, const uint64_t* nin,
+                              uint64_t* nout, int32_t* status, double* growth, void* stream) {
+    return do_refactor(1, 0, symbolic, n_lhs, 0, 0, n_nz, Ai, Aj, Ax, nullptr, nin, nullptr, nout,
+                       status, growth, stream);
+}
+int klujax_cuda_refactor_and_solve_f64(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz,
+                                       const int32_t* Ai, const int32_t* Aj, const double* Ax,
+                                       const double* b, const uint64_t* nin, double* x,
+                                       uint64_t* nout, int32_t* status, double* growth,
+                                       void* stream) {
+    return do_refactor(0, 1, symbolic, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, nin, x, nout,
+                       status, growth, stream);
+}
+int klujax_cuda_refactor_and_solve_c128(uint64_t symbolic, int n_lhs, int n_col, int n_rhs,
+                                        int n_nz, const int32_t* Ai, const int32_t* Aj,
+                                        const double* Ax, const double* b, const uint64_t* nin,
+                                        double* x, uint64_t* nout, int32_t* status, double* growth,
+                                        void* stream) {
+    return do_refactor(1, 1, symbolic, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, nin, x, nout,
+                       status, growth, stream);
+}
+
+// ---- solves with a numeric handle --------------------------------------------
+static int do_solve_numeric(int cx, int transpose, uint64_t symbolic, int n_numeric,
+                            const uint64_t* numeric, int n_lhs_b, int n_col, int n_rhs,
+                            const double* b, double* x, void* stream) {
+    Symbolic* S = sym_of(symbolic);
+    if (!S) return fail(KLU_INVALID, "symbolic pointer is null");
+    if (n_col != S->ord.n) return fail(KLU_INVALID, "n_col differs from the analysed matrix");
+    NumericBatch* nb = nullptr;
+    std::vector<int> idx;
+    bool identity = false;
+    int e = resolve_numeric(n_numeric, numeric, &nb, idx, identity);
+    if (e) return e;
+    if (nb->sym != S || nb->is_complex != cx)
+        return fail(KLU_INVALID, "numeric handle belongs to another symbolic handle / dtype");
+    // broadcast rules of klujax.cpp:1044-1059
+    const bool bc_num = (n_numeric == 1), bc_b = (n_lhs_b == 1);
+    int L;
+    if (!bc_num && !bc_b) {
+        if (n_numeric != n_lhs_b) return fail(KLU_INVALID, "numeric and b batch size mismatch");
+        L = n_numeric;
+    } else if (!bc_num) {
+        L = n_numeric;
+    } else if (!bc_b) {
+        L = n_lhs_b;
+    } else {
+        L = 1;
+    }
+    if (n_rhs <= 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DevBuf didx;
+    const bool ident = identity && (L == n_numeric);
+    if (!ident) {
+        e = upload_idx<int>(idx, L, didx, st);
+        if (e) return e;
+    }
+    Op op;
+    op.mode = transpose ? PM_TSOLVE : PM_SOLVE;
+    op.L = L;
+    op.r = n_rhs;
+    op.b = b;
+    op.b_stride = bc_b && L > 1 ? 0 : static_cast<long long>(n_col) * n_rhs;
+    op.x = x;
+    op.batch = nb;
+    op.sysidx_dev = ident ? nullptr : didx.as<int>();
+    op.st = st;
+    e = run_numeric(S, cx, op);
+    if (!ident) cudaStreamSynchronize(st);
+    return e;
+}
+#define DEF_SWN(name, cx, tr)                                                                     \
+    int name(uint64_t symbolic, int n_numeric, const uint64_t* numeric, int n_lhs_b, int n_col,   \
+             int n_rhs, const double* b, double* x, void* stream) {                               \
+        return do_solve_numeric(cx, tr, symbolic, n_numeric, numeric, n_lhs_b, n_col, n_rhs, b, x, \
+                                stream);                                                          \
+    }
+DEF_SWN(klujax_cuda_solve_with_numeric_f64, 0, 0)
+DEF_SWN(klujax_cuda_solve_with_numeric_c128, 1, 0)
+DEF_SWN(klujax_cuda_tsolve_with_numeric_f64, 0, 1)
+DEF_SWN(klujax_cuda_tsolve_with_numeric_c128, 1, 1)
+
+int klujax_cuda_free_numeric(int n, const uint64_t* numeric, int32_t* freed) {
+    if (freed) *freed = 1;  // the reference always reports 1 (klujax.cpp:1290)
+    std::vector<NumericBatch*> dead;
+    {
+        std::lock_guard<std::mutex> g(g_reg_mu);
+        for (int m = 0; m < n; ++m) {
+            if (!numeric || numeric[m] == 0) continue;
+            const uint32_t id = static_cast<uint32_t>(numeric[m] >> 32);
+            const int el = static_cast<int>(numeric[m] & 0xffffffffu) - 1;
+            auto it = g_batches.find(id);
+            if (it == g_batches.end()) continue;
+            NumericBatch* nb = it->second;
+            if (el < 0 || el >= nb->L || nb->freed[el]) continue;
+            nb->freed[el] = 1;
+            if (--nb->live == 0) {
+                g_batches.erase(it);
+                dead.push_back(nb);
+            }
+        }
+    }
+    for (NumericBatch* nb : dead) {
+        cudaDeviceSynchronize();  // storage may still be read by enqueued solves
+        delete nb;
+    }
+    return 0;
+}
+
+// ---- dot ----------------------------------------------------------------------
+int klujax_cuda_dot_f64(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai,
+                        const int32_t* Aj, const double* Ax, const double* x, double* b,
+                        void* stream) {
+    std::string err;
+    int rc = coo_spmm(0, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, x, b, static_cast<cudaStream_t>(stream), err);
+    return rc ? fail(rc, err) : 0;
+}
+int klujax_cuda_dot_c128(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai,
+                         const int32_t* Aj, const double* Ax, const double* x, double* b,
+                         void* stream) {
+    std::string err;
+    int rc = coo_spmm(1, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, x, b, static_cast<cudaStream_t>(stream), err);
+    return rc ? fail(rc, err) : 0;
+}
+
+}  // extern "C"

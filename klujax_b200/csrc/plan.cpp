@@ -1,0 +1,324 @@
+// plan.cpp — builds the static schedule (see plan.hpp).
+#include "plan.hpp"
+
+#include <algorithm>
+#include <numeric>
+
+namespace kb {
+
+namespace {
+
+std::vector<int> block_of_column(const Ordering& ord) {
+    std::vector<int> k1(ord.n);
+    for (int b = 0; b < ord.nblocks; ++b)
+        for (int k = ord.R[b]; k < ord.R[b + 1]; ++k) k1[k] = ord.R[b];
+    return k1;
+}
+
+}  // namespace
+
+void build_layout(const CscPattern& A, const Ordering& ord, const PivotPlan& piv, SlotLayout& lay) {
+    const int n = A.n;
+    lay = SlotLayout();
+    lay.n = n;
+    const std::vector<int> k1of = block_of_column(ord);
+    lay.col_begin.assign(n + 1, 0);
+    lay.diag_slot.assign(n, 0);
+    // slot order inside a column: U rows ascending, pivot, L rows ascending
+    for (int k = 0; k < n; ++k) {
+        const int k1 = k1of[k];
+        std::vector<int> ur(piv.Ui.begin() + piv.Up[k], piv.Ui.begin() + piv.Up[k + 1]);
+        std::vector<int> lr(piv.Li.begin() + piv.Lp[k], piv.Li.begin() + piv.Lp[k + 1]);
+        std::sort(ur.begin(), ur.end());
+        std::sort(lr.begin(), lr.end());
+        lay.col_begin[k] = static_cast<int>(lay.slot_row.size());
+        for (int j : ur) {
+            lay.slot_row.push_back(k1 + j);
+            lay.slot_col.push_back(k);
+        }
+        lay.diag_slot[k] = static_cast<int>(lay.slot_row.size());
+        lay.slot_row.push_back(k);
+        lay.slot_col.push_back(k);
+        for (int i : lr) {
+            lay.slot_row.push_back(k1 + i);
+            lay.slot_col.push_back(k);
+        }
+        lay.nnz_u += static_cast<int64_t>(ur.size());
+        lay.nnz_l += static_cast<int64_t>(lr.size());
+    }
+    lay.n_lu = static_cast<int>(lay.slot_row.size());
+    lay.col_begin[n] = lay.n_lu;
+    lay.n_off = static_cast<int>(piv.Offi.size());
+    lay.n_val = lay.n_lu + lay.n_off;
+    lay.slot_csc.assign(lay.n_val, -1);
+    for (int k = 0; k < n; ++k)
+        for (int p = piv.Offp[k]; p < piv.Offp[k + 1]; ++p) {
+            lay.slot_row.push_back(piv.Offi[p]);
+            lay.slot_col.push_back(k);
+            lay.slot_csc[lay.n_lu + p] = piv.Offsrc[p];
+        }
+    // where each entry of A lands
+    std::vector<int> pos(n, -1);
+    std::vector<int> csc_slot(A.rowidx.size(), -1);
+    for (int p = 0; p < lay.n_off; ++p) csc_slot[piv.Offsrc[p]] = lay.n_lu + p;
+    for (int k = 0; k < n; ++k) {
+        const int k1 = k1of[k];
+        for (int s = lay.col_begin[k]; s < lay.col_begin[k + 1]; ++s) pos[lay.slot_row[s]] = s;
+        const int col = ord.Q[k];
+        for (int p = A.colptr[col]; p < A.colptr[col + 1]; ++p) {
+            const int prow = piv.Pinv[A.rowidx[p]];
+            if (prow < k1) continue;  // off-diagonal block entry, already placed
+            const int s = pos[prow];
+            lay.slot_csc[s] = p;
+            csc_slot[p] = s;
+        }
+        for (int s = lay.col_begin[k]; s < lay.col_begin[k + 1]; ++s) pos[lay.slot_row[s]] = -1;
+    }
+    // (col,row)-sorted copy of A's pattern for the per-call COO -> slot map
+    lay.sorted_colptr = A.colptr;
+    lay.sorted_row.resize(A.rowidx.size());
+    lay.sorted_slot.resize(A.rowidx.size());
+    std::vector<int> ordv;
+    for (int j = 0; j < n; ++j) {
+        const int b = A.colptr[j], e = A.colptr[j + 1];
+        ordv.resize(e - b);
+        std::iota(ordv.begin(), ordv.end(), b);
+        std::sort(ordv.begin(), ordv.end(),
+                  [&](int x, int y) { return A.rowidx[x] < A.rowidx[y]; });
+        for (int t = 0; t < e - b; ++t) {
+            lay.sorted_row[b + t] = A.rowidx[ordv[t]];
+            lay.sorted_slot[b + t] = csc_slot[ordv[t]];
+        }
+    }
+    // row lists for the max-abs row scale factors
+    lay.rs_ptr.assign(n + 1, 0);
+    for (size_t p = 0; p < A.rowidx.size(); ++p) lay.rs_ptr[A.rowidx[p] + 1]++;
+    for (int i = 0; i < n; ++i) lay.rs_ptr[i + 1] += lay.rs_ptr[i];
+    lay.rs_slot.resize(A.rowidx.size());
+    std::vector<int> fill(lay.rs_ptr.begin(), lay.rs_ptr.end() - 1);
+    for (size_t p = 0; p < A.rowidx.size(); ++p) lay.rs_slot[fill[A.rowidx[p]]++] = csc_slot[p];
+}
+
+namespace {
+
+// Assigns levels while tasks are appended in a valid sequential order.
+struct Leveler {
+    std::vector<int> val_level, read_level;
+    TaskProgram& prog;
+    Leveler(int nidx, TaskProgram& p) : val_level(nidx, 0), read_level(nidx, 0), prog(p) {}
+    void add(uint8_t kind, int out, int div, const std::vector<std::pair<int, int>>& pairs) {
+        Task t;
+        t.kind = kind;
+        t.out = out;
+        t.div = div;
+        t.pbeg = static_cast<int>(prog.pa.size());
+        t.plen = static_cast<int>(pairs.size());
+        int lvl = std::max(val_level[out], read_level[out]);
+        if (div >= 0) lvl = std::max(lvl, val_level[div]);
+        for (const auto& pr : pairs) {
+            lvl = std::max(lvl, std::max(val_level[pr.first], val_level[pr.second]));
+            prog.pa.push_back(pr.first);
+            prog.pb.push_back(pr.second);
+        }
+        lvl += 1;
+        t.level = lvl;
+        if (div >= 0) read_level[div] = std::max(read_level[div], lvl);
+        for (const auto& pr : pairs) {
+            read_level[pr.first] = std::max(read_level[pr.first], lvl);
+            read_level[pr.second] = std::max(read_level[pr.second], lvl);
+        }
+        val_level[out] = lvl;
+        read_level[out] = 0;
+        prog.n_mac += t.plen;
+        prog.tasks.push_back(t);
+    }
+};
+
+}  // namespace
+
+void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
+                   int rc, TaskProgram& prog) {
+    const int n = lay.n;
+    prog = TaskProgram();
+    prog.mode = mode;
+    prog.rc = rc;
+    const bool do_factor = (mode == PM_FACTOR || mode == PM_FACTOR_SOLVE || mode == PM_FACTOR_TSOLVE);
+    const bool do_solve = (mode == PM_FACTOR_SOLVE || mode == PM_SOLVE);
+    const bool do_tsolve = (mode == PM_FACTOR_TSOLVE || mode == PM_TSOLVE);
+    const int nx = (do_solve || do_tsolve) ? n * rc : 0;
+    Leveler lv(lay.n_val + nx, prog);
+    const std::vector<int> k1of = block_of_column(ord);
+    auto xs = [&](int k, int c) { return lay.n_val + k * rc + c; };
+    std::vector<std::pair<int, int>> pairs;
+
+    if (do_factor) {
+        // Crout form of klu_refactor: every entry of column k is a dot product
+        // of finished entries of L (rows) and of U(:,k).
+        std::vector<int> pos(n, -1);
+        std::vector<std::vector<std::pair<int, int>>> dest;
+        for (int k = 0; k < n; ++k) {
+            const int cb = lay.col_begin[k], ce = lay.col_begin[k + 1], dg = lay.diag_slot[k];
+            if (ce - cb == 1) {
+                pairs.clear();
+                lv.add(TK_RECIP, dg, -1, pairs);
+                continue;
+            }
+            for (int s = cb; s < ce; ++s) pos[lay.slot_row[s]] = s;
+            dest.assign(ce - cb, {});
+            for (int su = cb; su < dg; ++su) {
+                const int j = lay.slot_row[su];  // U(j,k)
+                for (int sl = lay.diag_slot[j] + 1; sl < lay.col_begin[j + 1]; ++sl) {
+                    const int d = pos[lay.slot_row[sl]];  // (i,k) with L(i,j) != 0
+                    dest[d - cb].emplace_back(sl, su);
+                }
+            }
+            for (int s = cb; s < ce; ++s) {
+                const auto& pr = dest[s - cb];
+                if (s < dg) {
+                    if (!pr.empty()) lv.add(TK_SUB, s, -1, pr);
+                } else if (s == dg) {
+                    lv.add(TK_RECIP, s, -1, pr);
+                } else {
+                    lv.add(TK_MUL_TRACK, s, dg, pr);
+                }
+            }
+            for (int s = cb; s < ce; ++s) pos[lay.slot_row[s]] = -1;
+        }
+    }
+
+    if (do_solve) {
+        // row-wise views of L, U and the off-diagonal blocks
+        std::vector<std::vector<std::pair<int, int>>> lrow(n), urow(n), offrow(n);
+        for (int k = 0; k < n; ++k) {
+            for (int s = lay.col_begin[k]; s < lay.diag_slot[k]; ++s)
+                urow[lay.slot_row[s]].emplace_back(s, k);
+            for (int s = lay.diag_slot[k] + 1; s < lay.col_begin[k + 1]; ++s)
+                lrow[lay.slot_row[s]].emplace_back(s, k);
+        }
+        for (int i = 0; i < n; ++i) std::reverse(urow[i].begin(), urow[i].end());
+        for (int b = ord.nblocks - 1; b >= 0; --b)
+            for (int k = ord.R[b]; k < ord.R[b + 1]; ++k)
+                for (int p = piv.Offp[k]; p < piv.Offp[k + 1]; ++p)
+                    offrow[piv.Offi[p]].emplace_back(lay.n_lu + p, k);
+        // klu_solve: blocks last -> first; L then U inside a block
+        for (int b = ord.nblocks - 1; b >= 0; --b) {
+            const int k1 = ord.R[b], k2 = ord.R[b + 1];
+            if (k2 - k1 == 1) {
+                for (int c = 0; c < rc; ++c) {
+                    pairs.clear();
+                    for (auto& e : offrow[k1]) pairs.emplace_back(e.first, xs(e.second, c));
+                    lv.add(TK_MUL, xs(k1, c), lay.diag_slot[k1], pairs);
+                }
+                continue;
+            }
+            for (int i = k1; i < k2; ++i) {
+                if (offrow[i].empty() && lrow[i].empty()) continue;
+                for (int c = 0; c < rc; ++c) {
+                    pairs.clear();
+                    for (auto& e : offrow[i]) pairs.emplace_back(e.first, xs(e.second, c));
+                    for (auto& e : lrow[i]) pairs.emplace_back(e.first, xs(e.second, c));
+                    lv.add(TK_SUB, xs(i, c), -1, pairs);
+                }
+            }
+            for (int i = k2 - 1; i >= k1; --i)
+                for (int c = 0; c < rc; ++c) {
+                    pairs.clear();
+                    for (auto& e : urow[i]) pairs.emplace_back(e.first, xs(e.second, c));
+                    lv.add(TK_MUL, xs(i, c), lay.diag_slot[i], pairs);
+                }
+        }
+    }
+
+    if (do_tsolve) {
+        // klu_tsolve: blocks first -> last; U' then L' inside a block
+        for (int b = 0; b < ord.nblocks; ++b) {
+            const int k1 = ord.R[b], k2 = ord.R[b + 1];
+            for (int k = k1; k < k2; ++k)
+                for (int c = 0; c < rc; ++c) {
+                    pairs.clear();
+                    for (int p = piv.Offp[k]; p < piv.Offp[k + 1]; ++p)
+                        pairs.emplace_back(lay.n_lu + p, xs(piv.Offi[p], c));
+                    for (int s = lay.col_begin[k]; s < lay.diag_slot[k]; ++s)
+                        pairs.emplace_back(s, xs(lay.slot_row[s], c));
+                    lv.add(TK_MUL, xs(k, c), lay.diag_slot[k], pairs);
+                }
+            if (k2 - k1 == 1) continue;
+            for (int k = k2 - 1; k >= k1; --k) {
+                if (lay.diag_slot[k] + 1 == lay.col_begin[k + 1]) continue;
+                for (int c = 0; c < rc; ++c) {
+                    pairs.clear();
+                    for (int s = lay.diag_slot[k] + 1; s < lay.col_begin[k + 1]; ++s)
+                        pairs.emplace_back(s, xs(lay.slot_row[s], c));
+                    lv.add(TK_SUB, xs(k, c), -1, pairs);
+                }
+            }
+        }
+    }
+
+    // stable sort by level (longest dots first inside a level)
+    int maxlvl = 0;
+    for (const Task& t : prog.tasks) maxlvl = std::max(maxlvl, t.level);
+    prog.nlevels = maxlvl;
+    std::stable_sort(prog.tasks.begin(), prog.tasks.end(), [](const Task& a, const Task& b) {
+        if (a.level != b.level) return a.level < b.level;
+        return a.plen > b.plen;
+    });
+    // levels are 1-based: level_ptr[l] .. level_ptr[l+1] are the tasks of level l+1
+    prog.level_ptr.assign(maxlvl + 1, 0);
+    for (const Task& t : prog.tasks) prog.level_ptr[t.level]++;
+    for (int l = 0; l < maxlvl; ++l) prog.level_ptr[l + 1] += prog.level_ptr[l];
+}
+
+bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out) {
+    out = PackedProgram();
+    const int nx = (prog.mode == PM_FACTOR) ? 0 : lay.n * prog.rc;
+    out.zero_slot = lay.n_val + nx;
+    out.n_slots = out.zero_slot + 1;
+    if (out.n_slots > 16383) return false;  // 14-bit slot fields, 0x3FFF = no pivot operand
+    const uint32_t zero_word = (static_cast<uint32_t>(out.zero_slot) << 16) | out.zero_slot;
+    auto batch_cost = [](int p, int lg) { return 16 * ((p + (1 << lg) - 1) >> lg) + 33 * lg + 60; };
+    for (int l = 0; l < prog.nlevels; ++l) {
+        const int tb = prog.level_ptr[l], te = prog.level_ptr[l + 1];
+        // pick one lane-group width for the level: g lanes share one dot product
+        int best_lg = 0;
+        long best_cost = -1;
+        for (int lg = 0; lg <= 5; ++lg) {
+            const int per = 32 >> lg;
+            long cost = 0;
+            for (int t = tb; t < te; t += per) cost += batch_cost(prog.tasks[t].plen, lg);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                best_lg = lg;
+            }
+        }
+        const int g = 1 << best_lg, per = 32 >> best_lg;
+        for (int t0 = tb; t0 < te; t0 += per) {
+            const int t1 = std::min(te, t0 + per);
+            const int run = (prog.tasks[t0].plen + g - 1) / g;  // tasks are sorted by plen desc
+            if (run > 4095) return false;
+            const bool last = (t1 == te);
+            out.ctrl.push_back(static_cast<uint32_t>(run) | (static_cast<uint32_t>(best_lg) << 12) |
+                               (last ? (1u << 15) : 0u));
+            const size_t base = out.stream.size();
+            out.stream.resize(base + 32 * static_cast<size_t>(1 + run), zero_word);
+            for (int lane = 0; lane < 32; ++lane) out.stream[base + lane] = 0;  // TK_NOP
+            for (int t = t0; t < t1; ++t) {
+                const Task& tk = prog.tasks[t];
+                const int lead = (t - t0) * g;
+                const uint32_t div = tk.div >= 0 ? static_cast<uint32_t>(tk.div) : 0x3FFFu;
+                out.stream[base + lead] = (static_cast<uint32_t>(tk.kind) << 28) |
+                                          (static_cast<uint32_t>(tk.out) << 14) | div;
+                for (int q = 0; q < tk.plen; ++q) {
+                    const int lane = lead + (q % g), row = q / g;
+                    out.stream[base + 32 * static_cast<size_t>(1 + row) + lane] =
+                        (static_cast<uint32_t>(prog.pa[tk.pbeg + q]) << 16) |
+                        static_cast<uint32_t>(prog.pb[tk.pbeg + q]);
+                }
+            }
+            out.nbatch++;
+        }
+    }
+    return true;
+}
+
+}  // namespace kb

@@ -1,0 +1,87 @@
+// plan.hpp — the static elimination schedule derived once per symbolic handle.
+//
+// From the pivot plan (seed_lu.cpp) the host derives, ONCE, everything the
+// numeric kernels need; no kernel ever touches a sparsity structure again:
+//
+//   * a slot layout: every entry of L, U, the pivots and the BTF off-diagonal
+//     blocks gets one slot in a per-system value array V (fill-in included);
+//   * task lists in "dot" form (Crout):  V[out] = (V[out] - sum V[a]*V[b]) [*V[d]]
+//     for the refactorization (what klu_refactor does column by column,
+//     /root/reference/klujax.cpp:781,911) and for the triangular solves
+//     (klu_solve / klu_tsolve, klujax.cpp:315,445,573,917,1087,1220), including
+//     the BTF block back-substitution;
+//   * level sets of that task DAG (dependencies + anti-dependencies), which is
+//     the schedule both kernel regimes execute.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "symbolic.hpp"
+
+namespace kb {
+
+enum TaskKind : uint8_t {
+    TK_NOP = 0,
+    TK_SUB = 1,        // V[out] -= acc
+    TK_RECIP = 2,      // V[out]  = 1 / (V[out] - acc)        (pivot; singularity check)
+    TK_MUL = 3,        // V[out]  = (V[out] - acc) * V[div]   (solve with a pivot)
+    TK_MUL_TRACK = 4,  // same, and track max |V[out]|        (entry of L: growth certificate)
+};
+
+struct Task {
+    int out = 0, div = -1;
+    int pbeg = 0, plen = 0;
+    int level = 0;
+    uint8_t kind = TK_SUB;
+};
+
+// Slot layout of one system's value array.
+struct SlotLayout {
+    int n = 0;
+    int n_lu = 0;       // slots [0, n_lu): per pivot column k: U(:,k) | pivot | L(:,k)
+    int n_off = 0;      // slots [n_lu, n_lu+n_off): BTF off-diagonal entries
+    int n_val = 0;      // n_lu + n_off
+    std::vector<int> col_begin;   // n+1: first slot of column k
+    std::vector<int> diag_slot;   // n
+    std::vector<int> slot_row;    // n_val: global pivot row of the entry
+    std::vector<int> slot_col;    // n_val: global pivot column
+    std::vector<int> slot_csc;    // n_val: csc position of A landing here, -1 = fill-in
+    // A's pattern sorted by (col,row) -> slot, for the per-call COO map
+    std::vector<int> sorted_colptr, sorted_row, sorted_slot;
+    // row-scale lists: slots holding the entries of ORIGINAL row i
+    std::vector<int> rs_ptr, rs_slot;
+    int64_t nnz_l = 0, nnz_u = 0;  // strictly lower / strictly upper counts
+};
+
+enum ProgramMode : int {
+    PM_FACTOR = 0,         // refactor only                    (factor / refactor)
+    PM_FACTOR_SOLVE = 1,   // refactor + solve                 (solve, solve_with_symbol, refactor_and_solve)
+    PM_FACTOR_TSOLVE = 2,  // refactor + transpose solve       (tsolve_with_symbol)
+    PM_SOLVE = 3,          // solve from stored factors        (solve_with_numeric)
+    PM_TSOLVE = 4,         // transpose solve, stored factors  (tsolve_with_numeric)
+};
+
+// Leveled task list over the index space [0, n_val) U [n_val, n_val + n*rc):
+// value slots, then the right-hand-side slots X[k][c] = n_val + k*rc + c.
+struct TaskProgram {
+    int mode = 0, rc = 0, nlevels = 0;
+    std::vector<Task> tasks;       // sorted by level
+    std::vector<int> level_ptr;    // nlevels+1
+    std::vector<int> pa, pb;       // operand pairs
+    int64_t n_mac = 0;
+};
+
+void build_layout(const CscPattern& A, const Ordering& ord, const PivotPlan& piv, SlotLayout& lay);
+void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
+                   int rc, TaskProgram& prog);
+
+// Packed instruction stream of the shared-memory (small-matrix) regime: one warp
+// interprets it per system.  See kernels_small.cu for the decoding.
+struct PackedProgram {
+    std::vector<uint32_t> ctrl;    // per batch: run | log2g<<12 | sync<<15
+    std::vector<uint32_t> stream;  // per batch: 32 header words + run*32 operand words
+    int nbatch = 0, zero_slot = 0, n_slots = 0;  // n_slots includes X and the zero slot
+};
+bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out);
+
+}  // namespace kb
