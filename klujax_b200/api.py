@@ -1,0 +1,402 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Same names, argument meaning and error behaviour as /root/reference/klujax.py
+(`solve` :63, `dot` :99, `analyze` :297, `solve_with_symbol` :376,
+`tsolve_with_symbol` :416, `factor` :451, `refactor` :479,
+`solve_with_numeric` :523, `tsolve_with_numeric` :559, `refactor_and_solve` :612,
+`free_symbolic` :240, `free_numeric` :267, `coalesce` :134, `KLUHandleManager`
+:180), but the arrays are torch CUDA tensors and every call goes through the
+C-ABI of include/klujax_cuda.h instead of an XLA custom call.  torch is only
+used for device memory and streams.  There is no CPU fallback: without the CUDA
+library or a GPU these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Callable
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import KlujaxCudaError
+
+__all__ = [
+    "solve", "dot", "coalesce", "analyze", "factor", "refactor", "solve_with_symbol",
+    "tsolve_with_symbol", "solve_with_numeric", "tsolve_with_numeric", "refactor_and_solve",
+    "free_symbolic", "free_numeric", "KLUHandleManager", "KlujaxCudaError", "last_status",
+]
+
+_last = {"status": None, "growth": None}
+
+
+def last_status():
+    """(status int32[n_lhs], growth float64[n_lhs]) device tensors of the most recent
+    factorizing call: KLU-style per-system codes and the pivot-growth certificate."""
+    return _last["status"], _last["growth"]
+
+
+# --------------------------------------------------------------------------- helpers
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("klujax_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_tensor(a: Any) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        return a
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _is_complex(*ts: torch.Tensor) -> bool:
+    return any(t.is_complex() for t in ts)
+
+
+def _values(t: torch.Tensor, cx: bool) -> torch.Tensor:
+    """float64 / complex128, contiguous, on the device."""
+    return t.to(device=_device(), dtype=torch.complex128 if cx else torch.float64,
+                non_blocking=True).contiguous()
+
+
+def _indices(t: Any) -> torch.Tensor:
+    return _as_tensor(t).to(device=_device(), dtype=torch.int32, non_blocking=True).contiguous()
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr() if t is not None and t.numel() else None)
+
+
+def _handle_value(h: Any) -> np.ndarray:
+    h = getattr(h, "handle", h)
+    if isinstance(h, torch.Tensor):
+        h = h.cpu().numpy()
+    return np.ascontiguousarray(h, dtype=np.uint64)
+
+
+def _raise_if_failed(status: torch.Tensor, what: str, check: bool) -> None:
+    """The reference aborts the whole call on the first failing system
+    (klujax.cpp:311-314); reading the status array back is what that costs here."""
+    if not check:
+        return
+    bad = status != 0
+    if bool(bad.any()):
+        first = int(torch.nonzero(bad)[0])
+        code = int(status[first])
+        raise KlujaxCudaError(code, f"{what} failed (singular matrix?) at system {first}")
+
+
+def _canonical(Ax: torch.Tensor, x: torch.Tensor, x_name: str):
+    """Shape normalisation of klujax.py:1748-1849 (validate_args).  Returns
+    Ax[n_lhs, n_nz], x[n_lhs, n_col, n_rhs] and the caller-facing output shape."""
+    if Ax.ndim == 0 or Ax.ndim > 2:
+        raise ValueError("Ax should be 1D with shape (n_nz,) or 2D with shape (n_lhs, n_nz). "
+                         f"Got: Ax.shape={tuple(Ax.shape)}.")
+    if x.ndim == 0 or x.ndim > 3:
+        raise ValueError(f"{x_name} should be 1D (n_col,), 2D (n_col, n_rhs) or 3D "
+                         f"(n_lhs, n_col, n_rhs). Got: {x_name}.shape={tuple(x.shape)}.")
+    shape = tuple(x.shape)
+    if Ax.ndim == 1:
+        Ax = Ax[None, :]
+        if x.ndim == 1:
+            x = x[None, :, None]
+        elif x.ndim == 2:
+            x = x[None, :, :]
+    elif x.ndim == 1:
+        x = x[None, :, None]
+        shape = (Ax.shape[0], shape[0])
+    elif x.ndim == 2:
+        if Ax.shape[0] != x.shape[0] and Ax.shape[0] != 1 and x.shape[0] != 1:
+            raise ValueError("Ax (2D) and " + x_name + " (2D) should have their first shape index "
+                             f"`n_lhs` match. Got: Ax.shape={tuple(Ax.shape)}; "
+                             f"{x_name}.shape={tuple(x.shape)}.")
+        x = x[:, :, None]
+        if x.shape[0] == 1 and Ax.shape[0] > 0:
+            shape = (Ax.shape[0], *shape[1:])
+    if Ax.shape[0] != x.shape[0] and Ax.shape[0] != 1 and x.shape[0] != 1:
+        raise ValueError(f"Ax (2D) and {x_name} (3D) should have their first shape index `n_lhs` "
+                         f"match. Got: Ax.shape={tuple(Ax.shape)}; {x_name}.shape={tuple(x.shape)}.")
+    n_lhs = max(Ax.shape[0], x.shape[0])
+    Ax = Ax.expand(n_lhs, Ax.shape[1])
+    x = x.expand(n_lhs, x.shape[1], x.shape[2])
+    if len(shape) == 3 and shape[0] != n_lhs:
+        shape = (n_lhs, shape[1], shape[2])
+    return Ax, x, shape
+
+
+def _check_coo(Ai: torch.Tensor, Aj: torch.Tensor, Ax: torch.Tensor) -> None:
+    if Ai.ndim != 1:
+        raise ValueError(f"Ai should be 1D with shape (n_nz). Got: Ai.shape={tuple(Ai.shape)}.")
+    if Aj.ndim != 1:
+        raise ValueError(f"Aj should be 1D with shape (n_nz,). Got: Aj.shape={tuple(Aj.shape)}.")
+    if Ai.shape[0] != Aj.shape[0] or Ax.shape[-1] != Ai.shape[0]:
+        raise ValueError("n_nz mismatch between Ai, Aj and Ax: "
+                         f"{tuple(Ai.shape)}, {tuple(Aj.shape)}, {tuple(Ax.shape)}.")
+
+
+def _new_status(n_lhs: int):
+    dev = _device()
+    st = torch.empty(n_lhs, dtype=torch.int32, device=dev)
+    gr = torch.empty(n_lhs, dtype=torch.float64, device=dev)
+    _last["status"], _last["growth"] = st, gr
+    return st, gr
+
+
+def _suffix(cx: bool) -> str:
+    return "c128" if cx else "f64"
+
+
+# ----------------------------------------------------------------------- handle object
+class KLUHandleManager:
+    """RAII wrapper of a symbolic / numeric handle (klujax.py:180-237): frees on
+    close / __exit__ / __del__ when it is the owner."""
+
+    def __init__(self, handle: Any, free_callable: Callable | None, owner: bool = True) -> None:
+        self.handle = handle
+        self.free_callable = free_callable
+        self._owner = owner
+        self._freed = False
+
+    def close(self) -> None:
+        if self._freed:
+            return
+        if self._owner and self.free_callable:
+            try:
+                self.free_callable(self.handle)
+            except Exception:  # noqa: BLE001 - mirror of contextlib.suppress in the reference
+                pass
+        self._freed = True
+
+    def __enter__(self) -> "KLUHandleManager":
+        return self
+
+    def __exit__(self, *exc: Any) -> None:
+        self.close()
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+def free_symbolic(symbolic: Any, dependency: Any = None) -> int:  # noqa: ARG001
+    if isinstance(symbolic, KLUHandleManager):
+        symbolic.close()
+        return 0
+    return _cabi.free_symbolic(int(_handle_value(symbolic).reshape(-1)[0]))
+
+
+def free_numeric(numeric: Any, dependency: Any = None) -> int:  # noqa: ARG001
+    if isinstance(numeric, KLUHandleManager):
+        numeric.close()
+        return 0
+    return _cabi.free_numeric(_handle_value(numeric).reshape(-1))
+
+
+# ----------------------------------------------------------------------------- API
+def coalesce(Ai: Any, Aj: Any, Ax: Any):
+    """Sum duplicate COO entries and sort by (row, col) (klujax.py:134-174)."""
+    Ai, Aj, Ax = _as_tensor(Ai), _as_tensor(Aj), _as_tensor(Ax)
+    n = int(max(int(Ai.max()), int(Aj.max()))) + 1 if Ai.numel() else 1
+    key = Ai.to(torch.int64) * n + Aj.to(torch.int64)
+    ukey, inv = torch.unique(key, return_inverse=True)
+    out = torch.zeros((*Ax.shape[:-1], ukey.numel()), dtype=Ax.dtype, device=Ax.device)
+    out.index_add_(-1, inv, Ax)
+    return (ukey // n).to(Ai.dtype), (ukey % n).to(Aj.dtype), out
+
+
+def analyze(Ai: Any, Aj: Any, n_col: int) -> KLUHandleManager:
+    """Symbolic analysis (BTF + AMD) on the host; klujax.py:297-312."""
+    Ai_h = _as_tensor(Ai).detach().cpu().numpy().astype(np.int32)
+    Aj_h = _as_tensor(Aj).detach().cpu().numpy().astype(np.int32)
+    if Ai_h.ndim != 1 or Aj_h.ndim != 1 or Ai_h.size != Aj_h.size:
+        raise ValueError("Ai and Aj must be 1D arrays of equal length")
+    h = _cabi.analyze(Ai_h, Aj_h, int(n_col))
+    return KLUHandleManager(np.uint64(h), free_symbolic, owner=True)
+
+
+def _solve_symbol(fn: str, Ai, Aj, Ax, b, symbolic, check: bool):
+    Ai_t, Aj_t, Ax_t, b_t = _as_tensor(Ai), _as_tensor(Aj), _as_tensor(Ax), _as_tensor(b)
+    _check_coo(Ai_t, Aj_t, Ax_t)
+    Ax_t, b_t, shape = _canonical(Ax_t, b_t, "b")
+    cx = _is_complex(Ax_t, b_t)
+    Ai_d, Aj_d = _indices(Ai_t), _indices(Aj_t)
+    Ax_d, b_d = _values(Ax_t, cx), _values(b_t, cx)
+    L, n, r = b_d.shape
+    x = torch.empty_like(b_d)
+    st, gr = _new_status(L)
+    sym = int(_handle_value(symbolic).reshape(-1)[0])
+    f = getattr(_cabi.lib(), f"klujax_cuda_{fn}_{_suffix(cx)}")
+    _cabi.check(f(C.c_uint64(sym), L, n, r, Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d),
+                  _ptr(b_d), _ptr(x), _ptr(st), _ptr(gr), _stream()))
+    _raise_if_failed(st, "klu_factor", check)
+    return x.reshape(shape)
+
+
+def solve_with_symbol(Ai, Aj, Ax, b, symbolic, check: bool = True) -> torch.Tensor:
+    """Factor + solve with a precomputed symbolic analysis (klujax.py:376-393)."""
+    return _solve_symbol("solve_with_symbol", Ai, Aj, Ax, b, symbolic, check)
+
+
+def tsolve_with_symbol(Ai, Aj, Ax, b, symbolic, check: bool = True) -> torch.Tensor:
+    """Factor + transpose solve A^T x = b (plain transpose; klujax.py:416-440)."""
+    return _solve_symbol("tsolve_with_symbol", Ai, Aj, Ax, b, symbolic, check)
+
+
+def solve(Ai, Aj, Ax, b, check: bool = True) -> torch.Tensor:
+    """analyze + factor + solve in one call (klujax.py:63-96)."""
+    Ai_t, Aj_t, Ax_t, b_t = _as_tensor(Ai), _as_tensor(Aj), _as_tensor(Ax), _as_tensor(b)
+    _check_coo(Ai_t, Aj_t, Ax_t)
+    Ax_t, b_t, shape = _canonical(Ax_t, b_t, "b")
+    cx = _is_complex(Ax_t, b_t)
+    Ai_h = np.ascontiguousarray(Ai_t.detach().cpu().numpy(), dtype=np.int32)
+    Aj_h = np.ascontiguousarray(Aj_t.detach().cpu().numpy(), dtype=np.int32)
+    Ax_d, b_d = _values(Ax_t, cx), _values(b_t, cx)
+    L, n, r = b_d.shape
+    x = torch.empty_like(b_d)
+    st, gr = _new_status(L)
+    f = getattr(_cabi.lib(), f"klujax_cuda_solve_{_suffix(cx)}")
+    _cabi.check(f(L, n, r, int(Ai_h.size), _cabi.i32p(Ai_h), _cabi.i32p(Aj_h), _ptr(Ax_d), _ptr(b_d),
+                  _ptr(x), _ptr(st), _ptr(gr), _stream()))
+    _raise_if_failed(st, "klu_factor", check)
+    return x.reshape(shape)
+
+
+def dot(Ai, Aj, Ax, x) -> torch.Tensor:
+    """Batched COO sparse matrix times vector(s) (klujax.py:99-131)."""
+    Ai_t, Aj_t, Ax_t, x_t = _as_tensor(Ai), _as_tensor(Aj), _as_tensor(Ax), _as_tensor(x)
+    _check_coo(Ai_t, Aj_t, Ax_t)
+    Ax_t, x_t, shape = _canonical(Ax_t, x_t, "x")
+    cx = _is_complex(Ax_t, x_t)
+    Ai_d, Aj_d = _indices(Ai_t), _indices(Aj_t)
+    Ax_d, x_d = _values(Ax_t, cx), _values(x_t, cx)
+    L, n, r = x_d.shape
+    out = torch.empty_like(x_d)
+    f = getattr(_cabi.lib(), f"klujax_cuda_dot_{_suffix(cx)}")
+    _cabi.check(f(L, n, r, Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d), _ptr(x_d), _ptr(out),
+                  _stream()))
+    return out.reshape(shape)
+
+
+def factor(Ai, Aj, Ax, symbolic, check: bool = True) -> KLUHandleManager:
+    """Numeric factorization kept on the device behind u64 handles (klujax.py:451-468)."""
+    Ai_t, Aj_t, Ax_t = _as_tensor(Ai), _as_tensor(Aj), _as_tensor(Ax)
+    _check_coo(Ai_t, Aj_t, Ax_t)
+    if Ax_t.ndim == 1:
+        Ax_t = Ax_t[None, :]
+    if Ax_t.ndim != 2:
+        raise ValueError(f"Ax should be 1D or 2D. Got: Ax.shape={tuple(Ax_t.shape)}.")
+    cx = _is_complex(Ax_t)
+    Ai_d, Aj_d, Ax_d = _indices(Ai_t), _indices(Aj_t), _values(Ax_t, cx)
+    L = Ax_d.shape[0]
+    num = np.zeros(L, np.uint64)
+    st, gr = _new_status(L)
+    sym = int(_handle_value(symbolic).reshape(-1)[0])
+    f = getattr(_cabi.lib(), f"klujax_cuda_factor_{_suffix(cx)}")
+    _cabi.check(f(C.c_uint64(sym), L, Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d),
+                  _cabi.u64p(num), _ptr(st), _ptr(gr), _stream()))
+    try:
+        _raise_if_failed(st, "klu_factor", check)
+    except KlujaxCudaError:
+        _cabi.free_numeric(num)  # the reference frees the partial batch (klujax.cpp:684-687)
+        raise
+    return KLUHandleManager(num, free_numeric, owner=True)
+
+
+def refactor(Ai, Aj, Ax, numeric, symbolic, check: bool = True) -> KLUHandleManager:
+    """In-place numeric refactorization; returns a non-owning manager of the same
+    handles (klujax.py:479-512)."""
+    Ai_t, Aj_t, Ax_t = _as_tensor(Ai), _as_tensor(Aj), _as_tensor(Ax)
+    _check_coo(Ai_t, Aj_t, Ax_t)
+    if Ax_t.ndim == 1:
+        Ax_t = Ax_t[None, :]
+    cx = _is_complex(Ax_t)
+    Ai_d, Aj_d, Ax_d = _indices(Ai_t), _indices(Aj_t), _values(Ax_t, cx)
+    L = Ax_d.shape[0]
+    nin = _handle_value(numeric).reshape(-1)
+    if nin.size != L:
+        raise KlujaxCudaError(_cabi.KLU_INVALID, "numeric and Ax batch size mismatch")
+    nout = np.zeros_like(nin)
+    st, gr = _new_status(L)
+    sym = int(_handle_value(symbolic).reshape(-1)[0])
+    f = getattr(_cabi.lib(), f"klujax_cuda_refactor_{_suffix(cx)}")
+    _cabi.check(f(C.c_uint64(sym), L, Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d),
+                  _cabi.u64p(nin), _cabi.u64p(nout), _ptr(st), _ptr(gr), _stream()))
+    _raise_if_failed(st, "klu_refactor", check)
+    return KLUHandleManager(nout, free_numeric, owner=False)
+
+
+def refactor_and_solve(Ai, Aj, Ax, b, numeric, symbolic, check: bool = True):
+    """Fused refactor + solve (klujax.py:612-648).  Returns (x, non-owning numeric)."""
+    Ai_t, Aj_t, Ax_t, b_t = _as_tensor(Ai), _as_tensor(Aj), _as_tensor(Ax), _as_tensor(b)
+    _check_coo(Ai_t, Aj_t, Ax_t)
+    Ax_t, b_t, shape = _canonical(Ax_t, b_t, "b")
+    cx = _is_complex(Ax_t, b_t)
+    Ai_d, Aj_d = _indices(Ai_t), _indices(Aj_t)
+    Ax_d, b_d = _values(Ax_t, cx), _values(b_t, cx)
+    L, n, r = b_d.shape
+    nin = _handle_value(numeric).reshape(-1)
+    if nin.size != L:
+        raise KlujaxCudaError(_cabi.KLU_INVALID, "numeric and Ax batch size mismatch")
+    nout = np.zeros_like(nin)
+    x = torch.empty_like(b_d)
+    st, gr = _new_status(L)
+    sym = int(_handle_value(symbolic).reshape(-1)[0])
+    f = getattr(_cabi.lib(), f"klujax_cuda_refactor_and_solve_{_suffix(cx)}")
+    _cabi.check(f(C.c_uint64(sym), L, n, r, Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d),
+                  _ptr(b_d), _cabi.u64p(nin), _ptr(x), _cabi.u64p(nout), _ptr(st), _ptr(gr),
+                  _stream()))
+    _raise_if_failed(st, "klu_refactor", check)
+    return x.reshape(shape), KLUHandleManager(nout, free_numeric, owner=False)
+
+
+def _solve_numeric(fn: str, numeric, b, symbolic) -> torch.Tensor:
+    b_t = _as_tensor(b)
+    num = _handle_value(numeric).reshape(-1)
+    n_numeric = int(num.size)
+    # rank parsing of klujax.cpp:1011-1059: the 2-D case is decided by the numeric count
+    if b_t.ndim == 1:
+        b3 = b_t[None, :, None]
+    elif b_t.ndim == 2:
+        if n_numeric > 1 and b_t.shape[0] == n_numeric:
+            b3 = b_t[:, :, None]
+        else:
+            b3 = b_t[None, :, :]
+    elif b_t.ndim == 3:
+        b3 = b_t
+    else:
+        raise KlujaxCudaError(_cabi.KLU_INVALID, "b must be 1D, 2D, or 3D")
+    cx = _is_complex(b3)
+    b_d = _values(b3, cx)
+    Lb, n, r = b_d.shape
+    if n_numeric != 1 and Lb != 1 and n_numeric != Lb:
+        raise KlujaxCudaError(_cabi.KLU_INVALID, "numeric and b batch size mismatch")
+    L = max(n_numeric, Lb)
+    x = torch.empty((L, n, r), dtype=b_d.dtype, device=b_d.device)
+    sym = int(_handle_value(symbolic).reshape(-1)[0])
+    f = getattr(_cabi.lib(), f"klujax_cuda_{fn}_{_suffix(cx)}")
+    _cabi.check(f(C.c_uint64(sym), n_numeric, _cabi.u64p(num), Lb, n, r, _ptr(b_d), _ptr(x),
+                  _stream()))
+    # output has the rank of b (klujax.cpp:1061-1064); a broadcast batch keeps its size
+    if b_t.ndim == 1:
+        return x.reshape(n) if L == 1 else x.reshape(L, n)
+    if b_t.ndim == 2:
+        if n_numeric > 1 and b_t.shape[0] == n_numeric:
+            return x.reshape(L, n)
+        return x.reshape(n, r) if L == 1 else x
+    return x
+
+
+def solve_with_numeric(numeric, b, symbolic) -> torch.Tensor:
+    """Triangular solves with stored factors (klujax.py:523-546)."""
+    return _solve_numeric("solve_with_numeric", numeric, b, symbolic)
+
+
+def tsolve_with_numeric(numeric, b, symbolic) -> torch.Tensor:
+    """Transpose solve with stored factors (klujax.py:559-586)."""
+    return _solve_numeric("tsolve_with_numeric", numeric, b, symbolic)

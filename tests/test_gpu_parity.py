@@ -1,0 +1,323 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI by the API
+mirror (klujax_b200.api), against the CPU oracle on the same seeded inputs.
+Tolerances are BASELINE.json's: x within 1e-10 relative, residual
+||Ax-b||/||b|| <= 1e-12 on well-conditioned systems (float64 and complex128).
+The cases follow /root/reference/tests.py: shape matrix (:45-170), split API
+(:174-294), refactor (:401-527), transpose solves (:555-625),
+refactor_and_solve (:630-675)."""
+import os
+
+import numpy as np
+import pytest
+
+from klujax_b200 import synth
+from util import dense, golden, relerr, residual
+
+pytestmark = pytest.mark.gpu
+
+X_TOL = 1e-10
+RES_TOL = 1e-12
+DTYPES = [np.float64, np.complex128]
+
+
+@pytest.fixture(scope="module")
+def K():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import klujax_b200
+    from klujax_b200 import _cabi
+    _cabi.lib()  # fail loudly if the CUDA library is missing
+    return klujax_b200
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------ known answers
+def test_readme_known_answer(K):
+    g = golden()["readme_5x5"]
+    A = np.array(g["A_dense"], float)
+    Ai, Aj = np.nonzero(A)
+    x = np_(K.solve(Ai, Aj, A[Ai, Aj], np.array(g["b"], float)))
+    assert x.shape == (5,)
+    assert np.abs(x - np.array(g["x"])).max() < 1e-12
+
+
+def test_docs_batched_known_answers(K):
+    g = golden()
+    k = g["batched_multi_rhs"]
+    assert np.allclose(np_(K.solve(k["Ai"], k["Aj"], np.array(k["Ax"]), np.array(k["b"]))), k["x"], atol=1e-14)
+    k = g["batched_multi_matrix"]
+    assert np.allclose(np_(K.solve(k["Ai"], k["Aj"], np.array(k["Ax"]), np.array(k["b"]))), k["x"], atol=1e-14)
+    k = g["batched_broadcast_b"]
+    assert np.allclose(np_(K.solve(k["Ai"], k["Aj"], np.array(k["Ax"]), np.array(k["b"]))), k["x"], atol=1e-14)
+
+
+def test_golden_oracle_vectors(K):
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_vectors.npz"))
+    for nm in sorted({k.split("/")[0] for k in z.files}):
+        Ai, Aj, Ax, b = (z[f"{nm}/{k}"] for k in ("Ai", "Aj", "Ax", "b"))
+        with K.analyze(Ai, Aj, b.shape[1]) as sym:
+            assert relerr(np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym)), z[f"{nm}/x"]) < X_TOL
+            assert relerr(np_(K.tsolve_with_symbol(Ai, Aj, Ax, b, sym)), z[f"{nm}/xt"]) < X_TOL
+
+
+# ------------------------------------------------------------------ shape matrix
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_shapes_1d_2d_3d(K, oracle, dtype):
+    # (n_nz,) x (n_col,)
+    Ai, Aj, Ax, b = synth.ref_style_case(5, 15, 1, 1, dtype)
+    x = np_(K.solve(Ai, Aj, Ax[0], b[0, :, 0]))
+    assert x.shape == (5,)
+    assert relerr(x, oracle.solve(Ai, Aj, Ax, b)[0, :, 0]) < X_TOL
+    # (n_nz,) x (n_col, n_rhs)
+    Ai, Aj, Ax, b = synth.ref_style_case(5, 15, 1, 3, dtype)
+    x = np_(K.solve(Ai, Aj, Ax[0], b[0]))
+    assert x.shape == (5, 3) and relerr(x, oracle.solve(Ai, Aj, Ax, b)[0]) < X_TOL
+    # (n_lhs, n_nz) x (n_lhs, n_col)
+    Ai, Aj, Ax, b = synth.ref_style_case(5, 15, 4, 1, dtype)
+    x = np_(K.solve(Ai, Aj, Ax, b[:, :, 0]))
+    assert x.shape == (4, 5) and relerr(x, oracle.solve(Ai, Aj, Ax, b)[:, :, 0]) < X_TOL
+    # (n_lhs, n_nz) x (n_lhs, n_col, n_rhs)
+    Ai, Aj, Ax, b = synth.ref_style_case(5, 15, 3, 2, dtype)
+    x = np_(K.solve(Ai, Aj, Ax, b))
+    assert x.shape == (3, 5, 2) and relerr(x, oracle.solve(Ai, Aj, Ax, b)) < X_TOL
+    # (n_nz,) x (n_lhs, n_col, n_rhs): one matrix broadcast over the batch
+    x = np_(K.solve(Ai, Aj, Ax[0], b))
+    ref = oracle.solve(Ai, Aj, np.broadcast_to(Ax[:1], Ax.shape), b)
+    assert x.shape == (3, 5, 2) and relerr(x, ref) < X_TOL
+    # dense check, like tests.py:49-51
+    for m in range(3):
+        assert relerr(ref[m], np.linalg.solve(dense(Ai, Aj, Ax[0], 5), b[m])) < 1e-12
+
+
+def test_4d_raises_value_error(K):
+    Ai, Aj, Ax, b = synth.ref_style_case(5, 15, 2, 2, np.float64)
+    with pytest.raises(ValueError):
+        K.solve(Ai, Aj, Ax, b[None])
+    with pytest.raises(ValueError):
+        K.dot(Ai, Aj, Ax[None], b)
+
+
+# ------------------------------------------------------------------ split API
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(3, 8, 1, 1), (5, 15, 3, 2), (5, 15, 4, 6), (40, 160, 5, 3)])
+def test_every_entry_point_vs_oracle(K, oracle, dtype, shape):
+    n, nz, L, r = shape
+    Ai, Aj, Ax, b = synth.ref_style_case(n, nz, L, r, dtype)
+    so = oracle.analyze(Ai, Aj, n)
+    sym = K.analyze(Ai, Aj, n)
+    # the numeric call may present the COO entries in another order (klujax.py:319-321)
+    perm = np.random.default_rng(1).permutation(Ai.size)
+    xo = oracle.solve_with_symbol(Ai, Aj, Ax, b, so)
+    xto = oracle.solve_with_symbol(Ai, Aj, Ax, b, so, transpose=True)
+    assert relerr(np_(K.solve_with_symbol(Ai[perm], Aj[perm], Ax[:, perm], b, sym)), xo) < X_TOL
+    assert relerr(np_(K.tsolve_with_symbol(Ai, Aj, Ax, b, sym)), xto) < X_TOL
+    st, gr = K.last_status()
+    assert int(st.abs().max()) == 0 and float(gr.max()) <= 1000.0
+    num = K.factor(Ai, Aj, Ax, sym)
+    assert num.handle.shape == (L,) and num.handle.dtype == np.uint64 and (num.handle != 0).all()
+    assert relerr(np_(K.solve_with_numeric(num, b, sym)), xo) < X_TOL
+    assert relerr(np_(K.tsolve_with_numeric(num, b, sym)), xto) < X_TOL
+    # broadcast one factorization over the batch of b, and one b over the batch
+    no = oracle.factor(Ai, Aj, Ax, so)
+    one = K.KLUHandleManager(num.handle[:1], None, owner=False)
+    assert relerr(np_(K.solve_with_numeric(one, b, sym)), oracle.solve_with_numeric(so, no[:1], b)) < X_TOL
+    assert relerr(np_(K.solve_with_numeric(num, b[:1], sym)), oracle.solve_with_numeric(so, no, b[:1])) < X_TOL
+    # a reversed subset of the handles
+    if L > 1:
+        rev = K.KLUHandleManager(num.handle[::-1].copy(), None, owner=False)
+        assert relerr(np_(K.solve_with_numeric(rev, b, sym)), oracle.solve_with_numeric(so, no[::-1].copy(), b)) < X_TOL
+    # refactor with new values, in place, same handles back
+    Ax2 = Ax * 1.5 + 0.25 * np.roll(Ax, 1, axis=1)
+    num2 = K.refactor(Ai, Aj, Ax2, num, sym)
+    assert num2._owner is False and np.array_equal(num2.handle, num.handle)
+    x2o = oracle.solve_with_symbol(Ai, Aj, Ax2, b, so)
+    assert relerr(np_(K.solve_with_numeric(num2, b, sym)), x2o) < X_TOL
+    # fused refactor + solve
+    x3, num3 = K.refactor_and_solve(Ai, Aj, Ax, b, num, sym)
+    assert num3._owner is False and np.array_equal(num3.handle, num.handle)
+    assert relerr(np_(x3), xo) < X_TOL
+    assert relerr(np_(K.tsolve_with_numeric(num3, b, sym)), xto) < X_TOL
+    for m in range(L):
+        assert residual(Ai, Aj, Ax[m], np_(x3)[m], b[m], n) < RES_TOL
+    K.free_numeric(num)
+    K.free_symbolic(sym)
+    oracle.free_numeric(no)
+    oracle.free_symbolic(so)
+
+
+def test_solve_with_numeric_b_ranks(K, oracle):
+    Ai, Aj, Ax, b = synth.ref_style_case(5, 15, 3, 2, np.float64)
+    so = oracle.analyze(Ai, Aj, 5)
+    no = oracle.factor(Ai, Aj, Ax, so)
+    with K.analyze(Ai, Aj, 5) as sym, K.factor(Ai, Aj, Ax, sym) as num:
+        one = K.KLUHandleManager(num.handle[:1], None, owner=False)
+        # 1-D b with one numeric -> (n_col,)
+        x = np_(K.solve_with_numeric(one, b[0, :, 0], sym))
+        assert x.shape == (5,) and relerr(x, oracle.solve_with_numeric(so, no[:1], b[:1, :, :1])[0, :, 0]) < X_TOL
+        # 2-D b, first dim == number of numerics -> (n_lhs, n_col)   (klujax.cpp:1023)
+        x = np_(K.solve_with_numeric(num, b[:, :, 0], sym))
+        assert x.shape == (3, 5) and relerr(x, oracle.solve_with_numeric(so, no, b[:, :, :1])[:, :, 0]) < X_TOL
+        # 2-D b with a single numeric -> (n_col, n_rhs)
+        x = np_(K.solve_with_numeric(one, b[0], sym))
+        assert x.shape == (5, 2) and relerr(x, oracle.solve_with_numeric(so, no[:1], b[:1])[0]) < X_TOL
+    oracle.free_numeric(no)
+    oracle.free_symbolic(so)
+
+
+# ------------------------------------------------------------------ status path
+@pytest.mark.parametrize("regime", ["0", "1"])
+def test_singular_system_is_flagged_per_system(K, oracle, regime, monkeypatch):
+    monkeypatch.setenv("KLUJAX_CUDA_FORCE_REGIME", regime)
+    Ai, Aj, Ax, b = synth.ref_style_case(5, 15, 4, 1, np.float64)
+    Ax = Ax.copy()
+    Ax[2] = 0.0  # system 2 is singular; the seed (system 0) is fine
+    with K.analyze(Ai, Aj, 5) as sym:
+        with pytest.raises(K.KlujaxCudaError):
+            K.solve_with_symbol(Ai, Aj, Ax, b, sym)
+        x = np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym, check=False))
+        st, _ = K.last_status()
+        assert np_(st).tolist() == [0, 0, 1, 0]
+        so = oracle.analyze(Ai, Aj, 5)
+        keep = [0, 1, 3]
+        assert relerr(x[keep], oracle.solve_with_symbol(Ai, Aj, Ax[keep], b[keep], so)) < X_TOL
+        oracle.free_symbolic(so)
+        with pytest.raises(K.KlujaxCudaError):
+            K.factor(Ai, Aj, Ax, sym)
+
+
+def test_pattern_mismatch_is_invalid(K):
+    Ai, Aj, Ax, b = synth.ref_style_case(5, 15, 2, 1, np.float64)
+    with K.analyze(Ai, Aj, 5) as sym:
+        K.solve_with_symbol(Ai, Aj, Ax, b, sym)  # seeds
+        Ai2 = Ai.copy()
+        Ai2[0] = 7  # out of range
+        with pytest.raises(K.KlujaxCudaError) as ei:
+            K.solve_with_symbol(Ai2, Aj, Ax, b, sym)
+        assert ei.value.code == -3
+
+
+# ------------------------------------------------------------------ the named configs
+@pytest.mark.parametrize("n,seed,r", [(64, 1, 1), (64, 1, 4), (128, 2, 1), (128, 2, 6)])
+def test_sax_configs_vs_oracle(K, oracle, n, seed, r):
+    """cfg2 / cfg5 shape (SAX photonic S-matrix systems, complex128)."""
+    L = 96
+    pat = synth.SaxPattern(n, seed=seed)
+    Ax = pat.values(0, L)
+    rng = np.random.default_rng(9)
+    b = rng.standard_normal((L, n, r)) + 1j * rng.standard_normal((L, n, r))
+    so = oracle.analyze(pat.Ai, pat.Aj, n)
+    with K.analyze(pat.Ai, pat.Aj, n) as sym:
+        x = np_(K.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, sym))
+        xt = np_(K.tsolve_with_symbol(pat.Ai, pat.Aj, Ax, b, sym))
+        st, gr = K.last_status()
+        assert int(st.abs().max()) == 0 and float(gr.max()) <= 1000.0
+    assert relerr(x, oracle.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, so)) < X_TOL
+    assert relerr(xt, oracle.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, so, transpose=True)) < X_TOL
+    for m in range(0, L, 7):
+        assert residual(pat.Ai, pat.Aj, Ax[m], x[m], b[m], n) < RES_TOL
+        assert residual(pat.Ai, pat.Aj, Ax[m], xt[m], b[m], n, transpose=True) < RES_TOL
+    oracle.free_symbolic(so)
+
+
+def test_cfg1_random_dd_solve(K, oracle):
+    """cfg1: klujax.solve float64, n=1000, nnz~5000, n_lhs=1 (level-scheduled regime)."""
+    Ai, Aj, Ax = synth.random_dd()
+    b = np.random.default_rng(1).standard_normal((1000,))
+    x = np_(K.solve(Ai, Aj, Ax[0], b))
+    xo = oracle.solve(Ai, Aj, Ax, b[None, :, None])[0, :, 0]
+    assert relerr(x, xo) < X_TOL
+    assert residual(Ai, Aj, Ax[0], x[:, None], b[:, None], 1000) < RES_TOL
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_level_regime_mna_btf(K, oracle, dtype):
+    """cfg4 shape at reduced n: BTF blocks, refactor per step, solve + transpose solve."""
+    pat = synth.MnaPattern(n=3000)
+    n, L = pat.n, 5
+    Ax0 = pat.values(0, L).astype(dtype)
+    if dtype is np.complex128:
+        Ax0 = Ax0 * (1 + 0.05j)
+    rng = np.random.default_rng(4)
+    b = rng.standard_normal((L, n, 2)).astype(dtype)
+    so = oracle.analyze(pat.Ai, pat.Aj, n)
+    no = oracle.factor(pat.Ai, pat.Aj, Ax0, so)
+    with K.analyze(pat.Ai, pat.Aj, n) as sym, K.factor(pat.Ai, pat.Aj, Ax0, sym) as num:
+        for t in (1, 2):
+            Ax = pat.values(t, L).astype(dtype)
+            if dtype is np.complex128:
+                Ax = Ax * (1 + 0.05j)
+            num2 = K.refactor(pat.Ai, pat.Aj, Ax, num, sym)
+            no = oracle.refactor(pat.Ai, pat.Aj, Ax, so, no)
+            x = np_(K.solve_with_numeric(num2, b, sym))
+            xt = np_(K.tsolve_with_numeric(num2, b, sym))
+            assert relerr(x, oracle.solve_with_numeric(so, no, b)) < X_TOL
+            assert relerr(xt, oracle.solve_with_numeric(so, no, b, transpose=True)) < X_TOL
+            assert residual(pat.Ai, pat.Aj, Ax[1], x[1], b[1], n) < RES_TOL
+        x3, _ = K.refactor_and_solve(pat.Ai, pat.Aj, Ax0, b, num, sym)
+        assert relerr(np_(x3), oracle.solve_with_symbol(pat.Ai, pat.Aj, Ax0, b, so)) < X_TOL
+    oracle.free_numeric(no)
+    oracle.free_symbolic(so)
+
+
+def test_level_regime_poisson_multi_rhs(K, oracle):
+    """cfg3 shape at reduced grid: factor once, solve_with_numeric with many RHS."""
+    g, L, r = 48, 3, 40
+    Ai, Aj, Ax = synth.poisson2d(g, L)
+    n = g * g
+    b = np.random.default_rng(3).standard_normal((L, n, r))
+    so = oracle.analyze(Ai, Aj, n)
+    no = oracle.factor(Ai, Aj, Ax, so)
+    with K.analyze(Ai, Aj, n) as sym, K.factor(Ai, Aj, Ax, sym) as num:
+        x = np_(K.solve_with_numeric(num, b, sym))
+    assert relerr(x, oracle.solve_with_numeric(so, no, b)) < X_TOL
+    assert residual(Ai, Aj, Ax[2], x[2], b[2], n) < RES_TOL
+    oracle.free_numeric(no)
+    oracle.free_symbolic(so)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_level_regime_on_small_cases(K, oracle, dtype, monkeypatch):
+    """Same answers from both regimes on the reference's tiny test matrices."""
+    monkeypatch.setenv("KLUJAX_CUDA_FORCE_REGIME", "1")
+    Ai, Aj, Ax, b = synth.ref_style_case(20, 60, 37, 3, dtype)
+    so = oracle.analyze(Ai, Aj, 20)
+    with K.analyze(Ai, Aj, 20) as sym:
+        assert relerr(np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym)), oracle.solve_with_symbol(Ai, Aj, Ax, b, so)) < X_TOL
+        assert relerr(np_(K.tsolve_with_symbol(Ai, Aj, Ax, b, sym)),
+                      oracle.solve_with_symbol(Ai, Aj, Ax, b, so, transpose=True)) < X_TOL
+    oracle.free_symbolic(so)
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_cfg5_full_size_properties(K):
+    """n_lhs = 65536, n_col = 128, complex128: too big for the oracle in seconds, so
+    check size-independent properties: residual on every system, linearity, status."""
+    import torch
+    n, L = 128, 65536
+    pat = synth.SaxPattern(n, seed=2)
+    Ax = torch.from_numpy(pat.values_fast(L)).cuda()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    b = torch.randn(L, n, 1, dtype=torch.float64, device="cuda", generator=g).to(torch.complex128)
+    Ai, Aj = torch.from_numpy(pat.Ai).cuda(), torch.from_numpy(pat.Aj).cuda()
+    with K.analyze(pat.Ai, pat.Aj, n) as sym:
+        x = K.solve_with_symbol(Ai, Aj, Ax, b, sym)
+        st, gr = K.last_status()
+        assert int(st.abs().max()) == 0 and float(gr.max()) <= 1000.0
+        x2 = K.solve_with_symbol(Ai, Aj, Ax, 3.0 * b, sym)
+    Ax_x = torch.zeros_like(b)
+    Ax_x.index_add_(1, Ai.long(), Ax[:, :, None] * x[:, Aj.long(), :])
+    res = (torch.linalg.vector_norm(Ax_x - b, dim=1) / torch.linalg.vector_norm(b, dim=1)).max()
+    assert float(res) < RES_TOL
+    assert float((x2 - 3.0 * x).abs().max() / x.abs().max()) < 1e-13
+
+
+# ------------------------------------------------------------------ dot (next: f1)
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dot_vs_dense(K, dtype):
+    Ai, Aj, Ax, x = synth.ref_style_case(5, 15, 3, 2, dtype)
+    got = np_(K.dot(Ai, Aj, Ax, x))
+    for m in range(3):
+        assert relerr(got[m], dense(Ai, Aj, Ax[m], 5) @ x[m]) < 1e-13

@@ -1,0 +1,113 @@
+"""Host side of the product against the oracle, no GPU: the C-ABI library loads
+and exports everything include/klujax_cuda.h declares; the symbolic stage gives
+the oracle's P / Q / R / Pnum and L/U patterns bit-exactly; the static schedule
+is consistent."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from klujax_b200 import synth
+
+
+def test_library_exports_every_declared_symbol(cabi):
+    names = cabi.declared_symbols()
+    assert len(names) == 27
+    lib = cabi.lib()
+    for nm in names:
+        assert hasattr(lib, nm), nm
+    assert lib.klujax_cuda_abi_version() == 1
+
+
+def _cases():
+    A = np.array([[2, 3, 0, 0, 0], [3, 0, 4, 0, 6], [0, -1, -3, 2, 0], [0, 0, 1, 0, 0], [0, 4, 2, 0, 1]], float)
+    Ai, Aj = np.nonzero(A)
+    yield "readme5", Ai.astype(np.int32), Aj.astype(np.int32), A[Ai, Aj], 5
+    for dt in (np.float64, np.complex128):
+        for n, nz in ((3, 8), (5, 15), (20, 60), (50, 200)):
+            Ai, Aj, Ax, _ = synth.ref_style_case(n, nz, 1, 1, dt)
+            yield f"ref{n}_{np.dtype(dt).name}", Ai, Aj, Ax[0], n
+    Ai, Aj, Ax = synth.random_dd()
+    yield "cfg1", Ai, Aj, Ax[0], 1000
+    for n, seed in ((64, 1), (128, 2)):
+        p = synth.SaxPattern(n, seed=seed)
+        yield f"sax{n}", p.Ai, p.Aj, p.values(0, 1)[0], n
+    p = synth.MnaPattern(n=4000)
+    yield "mna4000", p.Ai, p.Aj, p.values(0, 1)[0], p.n
+    p = synth.MnaPattern(n=1500, symmetric_hide=False)
+    yield "mna1500_unsym", p.Ai, p.Aj, p.values(0, 1)[0], p.n
+    Ai, Aj, Ax = synth.poisson2d(40, 1)
+    yield "poisson40", Ai, Aj, Ax[0], 1600
+
+
+@pytest.mark.parametrize("case", list(_cases()), ids=lambda c: c[0])
+def test_permutations_and_patterns_match_oracle(oracle, cabi, case):
+    _, Ai, Aj, Ax0, n = case
+    so = oracle.analyze(Ai, Aj, n)
+    sp = cabi.analyze(Ai, Aj, n)
+    io, ip = oracle.symbolic_info(so), cabi.symbolic_perm(sp)
+    for k in ("nblocks", "maxblock", "nzoff", "structural_rank"):
+        assert io[k] == ip[k], k
+    for k in ("P", "Q", "R"):
+        assert np.array_equal(io[k], ip[k]), k
+    cabi.seed_host(sp, Ax0)
+    pp = cabi.symbolic_pattern(sp, np.iscomplexobj(Ax0))
+    num = oracle.factor(Ai, Aj, Ax0[None], so)
+    ni = oracle.numeric_info(num[0])
+    assert np.array_equal(ni["Pnum"], pp["Pnum"])
+    assert ni["nnz_l_off"] == pp["nnz_l"] and ni["nnz_u_off"] == pp["nnz_u"]
+    assert ni["noffdiag"] == pp["noffdiag"]
+    for k in range(n):  # column patterns as sets (KLU leaves them unsorted)
+        lo = np.sort(ni["Li"][ni["Lp"][k]:ni["Lp"][k] + ni["Llen"][k]])
+        uo = np.sort(ni["Ui"][ni["Up"][k]:ni["Up"][k] + ni["Ulen"][k]])
+        assert np.array_equal(lo, pp["Li"][pp["Lp"][k]:pp["Lp"][k + 1]])
+        assert np.array_equal(uo, pp["Ui"][pp["Up"][k]:pp["Up"][k + 1]])
+    assert pp["levels"] > 0 and pp["mac"] >= 0
+    oracle.free_numeric(num)
+    oracle.free_symbolic(so)
+    assert cabi.free_symbolic(sp) == 1
+
+
+def test_regime_choice(cabi):
+    p = synth.SaxPattern(128, seed=2)
+    s = cabi.analyze(p.Ai, p.Aj, 128)
+    cabi.seed_host(s, p.values(0, 1)[0])
+    assert cabi.symbolic_info(s, True)["regime"] == 0  # shared-memory regime
+    cabi.free_symbolic(s)
+    Ai, Aj, Ax = synth.random_dd()
+    s = cabi.analyze(Ai, Aj, 1000)
+    cabi.seed_host(s, Ax[0])
+    assert cabi.symbolic_info(s, False)["regime"] == 1  # level-scheduled regime
+    cabi.free_symbolic(s)
+
+
+def test_error_conventions(cabi):
+    # null symbolic: nothing to free, status 0 (klujax.cpp:1302-1305)
+    assert cabi.free_symbolic(0) == 0
+    # out-of-range index -> error like klujax.cpp:1351-1354
+    with pytest.raises(cabi.KlujaxCudaError):
+        cabi.analyze(np.array([0, 5], np.int32), np.array([0, 1], np.int32), 2)
+    # duplicates are rejected at factor time (KLU_scale), i.e. when seeding
+    s = cabi.analyze(np.array([0, 0, 1], np.int32), np.array([0, 0, 1], np.int32), 2)
+    with pytest.raises(cabi.KlujaxCudaError) as ei:
+        cabi.seed_host(s, np.ones(3))
+    assert ei.value.code == cabi.KLU_INVALID
+    cabi.free_symbolic(s)
+    # singular seed system
+    s = cabi.analyze(np.array([0, 1, 0, 1], np.int32), np.array([0, 0, 1, 1], np.int32), 2)
+    with pytest.raises(cabi.KlujaxCudaError) as ei:
+        cabi.seed_host(s, np.array([1.0, 2.0, 2.0, 4.0]))
+    assert ei.value.code == cabi.KLU_SINGULAR
+    cabi.free_symbolic(s)
+    # stale / null numeric handles are ignored by free_numeric (klujax.cpp:1284)
+    assert cabi.free_numeric(np.zeros(3, np.uint64)) == 1
+
+
+def test_no_cpu_fallback_in_api():
+    """Operators must raise without a GPU rather than compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import klujax_b200
+    with pytest.raises(RuntimeError):
+        klujax_b200.solve(np.array([0], np.int32), np.array([0], np.int32), np.ones(1), np.ones(1))
