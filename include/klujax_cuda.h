@@ -152,8 +152,9 @@ int klujax_cuda_seed_host(uint64_t symbolic, int is_complex, const double* Ax_ho
 /* sizes: out[0]=n out[1]=nblocks out[2]=maxblock out[3]=nzoff out[4]=structural_rank
  *        out[5]=nnz(L) strictly lower  out[6]=nnz(U) strictly upper  out[7]=seeded(0/1)
  *        out[8]=regime (0 shared-memory, 1 level-scheduled)  out[9]=levels of factor+solve
- *        out[10]=multiply-adds of one refactor  out[11]=noffdiag */
-int klujax_cuda_symbolic_info(uint64_t symbolic, int is_complex, int64_t* out12);
+ *        out[10]=multiply-adds of one refactor  out[11]=noffdiag
+ *        out[12]=batches, out[13]=32-bit words of the packed factor+solve program (regime 0) */
+int klujax_cuda_symbolic_info(uint64_t symbolic, int is_complex, int64_t* out14);
 /* P[n], Q[n], R[nblocks+1] of the analysis; any pointer may be NULL */
 int klujax_cuda_symbolic_perm(uint64_t symbolic, int32_t* P, int32_t* Q, int32_t* R);
 /* after seeding: Pnum[n]; CSC patterns of L and U in pivot order with block-local,

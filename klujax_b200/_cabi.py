@@ -96,11 +96,11 @@ def seed_host(h: int, Ax0: np.ndarray) -> None:
 
 
 _INFO_KEYS = ("n", "nblocks", "maxblock", "nzoff", "structural_rank", "nnz_l", "nnz_u", "seeded",
-              "regime", "levels", "mac", "noffdiag")
+              "regime", "levels", "mac", "noffdiag", "nbatch", "stream_words")
 
 
 def symbolic_info(h: int, is_complex: bool) -> dict:
-    out = np.zeros(12, np.int64)
+    out = np.zeros(14, np.int64)
     check(lib().klujax_cuda_symbolic_info(C.c_uint64(int(h)), int(is_complex),
                                           out.ctypes.data_as(C.POINTER(C.c_int64))))
     return dict(zip(_INFO_KEYS, (int(v) for v in out)))

@@ -89,10 +89,11 @@ enum SmallFlags : int {
 
 struct SmallArgs {
     // packed programs: [0] first right-hand-side chunk (may include the refactor),
-    // [1] further chunks (solve only)
-    const uint32_t* ctrl[2];
+    // [1] further right-hand-side chunks (solve only)
     const uint32_t* stream[2];
-    int nbatch[2];
+    int nchunks[2];
+    uint32_t zero_word;
+    int W;                   // systems (= consumer warps) per CTA
     int n, n_val, n_slots, zero_slot, rc, nz, flags;
     const int* coo_dst;      // [nz] slot of each COO entry of this call, -1 = not in pattern
     const int* pattern_bad;  // device flag set by the COO map
@@ -114,120 +115,191 @@ struct SmallArgs {
     int L;
 };
 
-// One batch of the packed program: `run` operand lines, an optional lane-group
-// reduction, then every leading lane finishes its task.
-template <typename T>
-__device__ __forceinline__ void run_program(typename Sc<T>::V* __restrict__ V,
-                                            const uint32_t* __restrict__ ctrl,
-                                            const uint32_t* __restrict__ stream, int nbatch,
-                                            int lane, bool& bad, double& gmax) {
-    using S = Sc<T>;
-    using V_t = typename S::V;
-    const uint32_t* sp = stream + lane;
-    uint32_t c_next = nbatch > 0 ? __ldg(ctrl) : 0u;
-    uint32_t h_next = nbatch > 0 ? __ldg(sp) : 0u;
-    for (int bi = 0; bi < nbatch; ++bi) {
-        const uint32_t c = c_next, h = h_next;
-        const int run = c & 0xFFF, lg = (c >> 12) & 7;
-        const uint32_t* ops = sp + 32;
-        sp = ops + 32 * run;
-        if (bi + 1 < nbatch) {  // prefetch the next batch header
-            c_next = __ldg(ctrl + bi + 1);
-            h_next = __ldg(sp);
-        }
-        const int kind = h >> 28, out = (h >> 14) & 0x3FFF, dv = h & 0x3FFF;
-        V_t vo = S::zero(), vd = S::zero();
-        if (kind) vo = S::ld(V + out);
-        if (kind >= 3) vd = S::ld(V + dv);
-        V_t acc = S::zero();
-        int q = 0;
-        for (; q + 4 <= run; q += 4) {
-            const uint32_t w0 = __ldg(ops + 32 * q), w1 = __ldg(ops + 32 * (q + 1)),
-                           w2 = __ldg(ops + 32 * (q + 2)), w3 = __ldg(ops + 32 * (q + 3));
-            const V_t a0 = S::ld(V + (w0 >> 16)), b0 = S::ld(V + (w0 & 0xFFFF));
-            const V_t a1 = S::ld(V + (w1 >> 16)), b1 = S::ld(V + (w1 & 0xFFFF));
-            const V_t a2 = S::ld(V + (w2 >> 16)), b2 = S::ld(V + (w2 & 0xFFFF));
-            const V_t a3 = S::ld(V + (w3 >> 16)), b3 = S::ld(V + (w3 & 0xFFFF));
-            S::fma_acc(acc, a0, b0);
-            S::fma_acc(acc, a1, b1);
-            S::fma_acc(acc, a2, b2);
-            S::fma_acc(acc, a3, b3);
-        }
-        for (; q < run; ++q) {
-            const uint32_t w = __ldg(ops + 32 * q);
-            S::fma_acc(acc, S::ld(V + (w >> 16)), S::ld(V + (w & 0xFFFF)));
-        }
-        if (lg) {
-            const int g = 1 << lg;
-            for (int o = g >> 1; o > 0; o >>= 1) acc = S::add(acc, S::shfl_down(acc, o, g));
-        }
-        if (kind) {
-            V_t t = S::sub(vo, acc);
-            if (kind == TK_RECIP) {
-                bad |= S::bad_pivot(t);
-                t = S::recip(t);
-            } else if (kind >= TK_MUL) {
-                t = S::mul(t, vd);
-                if (kind == TK_MUL_TRACK) gmax = fmax(gmax, S::mag2(t));
-            }
-            S::st(V + out, t);
-        }
-        if (c & 0x8000u) __syncwarp();
-    }
+constexpr int kRingBufs = 3;                                   // chunks in flight per CTA
+constexpr int kChunkWords = kChunkLines * 32;
+constexpr int kChunkBytes = kChunkWords * 4;
+constexpr int kRingBytes = kRingBufs * kChunkBytes;
+constexpr int kSmallHeaderBytes = kRingBytes + 128;            // ring + mbarriers
+
+// ---- mbarrier / TMA bulk copy (sm_90+ PTX; the schedule ring is fed by cp.async.bulk) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
 }
 
+// One batch: `run` operand lines, an optional lane-group reduction, then every leading
+// lane finishes its task.  `line` points at the batch header in the shared-memory ring.
 template <typename T>
-__global__ void __launch_bounds__(32) small_kernel(const SmallArgs a) {
+__device__ __forceinline__ void run_batch(typename Sc<T>::V* __restrict__ V,
+                                          const uint32_t* __restrict__ line, uint32_t cw,
+                                          uint32_t zero_word, bool& bad, double& gmax) {
     using S = Sc<T>;
     using V_t = typename S::V;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    V_t* V = reinterpret_cast<V_t*>(smem_raw);
+    const int run = cw & 0xFF, lg = (cw >> 8) & 7;
+    const uint32_t h = line[0];
+    const int kind = h >> 28, out = (h >> 14) & 0x3FFF, dv = h & 0x3FFF;
+    V_t vo = S::zero(), vd = S::zero();
+    if (kind) vo = S::ld(V + out);
+    if (kind >= TK_MUL) vd = S::ld(V + dv);
+    V_t acc0 = S::zero(), acc1 = S::zero();
+    const uint32_t* ops = line + 32;
+    int q = 0;
+    for (; q + 2 <= run; q += 2) {
+        const uint32_t w0 = ops[32 * q], w1 = ops[32 * q + 32];
+        if (w0 != zero_word) S::fma_acc(acc0, S::ld(V + (w0 >> 16)), S::ld(V + (w0 & 0xFFFF)));
+        if (w1 != zero_word) S::fma_acc(acc1, S::ld(V + (w1 >> 16)), S::ld(V + (w1 & 0xFFFF)));
+    }
+    if (q < run) {
+        const uint32_t w0 = ops[32 * q];
+        if (w0 != zero_word) S::fma_acc(acc0, S::ld(V + (w0 >> 16)), S::ld(V + (w0 & 0xFFFF)));
+    }
+    V_t acc = S::add(acc0, acc1);
+    if (lg) {
+        const int g = 1 << lg;
+        for (int o = g >> 1; o > 0; o >>= 1) acc = S::add(acc, S::shfl_down(acc, o, g));
+    }
+    if (kind) {
+        V_t t = S::sub(vo, acc);
+        if (kind == TK_RECIP) {
+            bad |= S::bad_pivot(t);
+            t = S::recip(t);
+        } else if (kind >= TK_MUL) {
+            t = S::mul(t, vd);
+            if (kind == TK_MUL_TRACK) gmax = fmax(gmax, S::mag2(t));
+        }
+        S::st(V + out, t);
+    }
+    if (cw & 0x800u) __syncwarp();
+}
+
+// CTA = W consumer warps (one system each, private value array in shared memory) + one
+// producer warp that streams the packed schedule through a ring of kRingBufs chunks with TMA
+// bulk copies; full/empty mbarriers pace it.  All consumer warps of a CTA walk the same
+// program, so the schedule is read from L2 once per CTA, not once per system.
+template <typename T>
+__global__ void __launch_bounds__(544) small_kernel(const SmallArgs a) {
+    using S = Sc<T>;
+    using V_t = typename S::V;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kRingBytes);
+    uint64_t* empty = full + kRingBufs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = a.W;
+    const int n = a.n, rc = a.rc, r = a.r;
+    const size_t per_sys = (static_cast<size_t>(a.n_slots) * sizeof(V_t) + static_cast<size_t>(n) * 8 + 15) & ~size_t(15);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kRingBufs; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, W);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int per_round = gridDim.x * W;
+    const int rounds = (a.L + per_round - 1) / per_round;
+    const int nrhs_chunks = (a.flags & SF_SOLVE) ? (r + rc - 1) / rc : 1;
+
+    if (warp == W) {
+        // ---------------- producer warp: one elected lane feeds the ring ----------------
+        if (lane == 0) {
+            uint32_t cc = 0;
+            for (int rd = 0; rd < rounds; ++rd)
+                for (int ch = 0; ch < nrhs_chunks; ++ch) {
+                    const int pi = ch == 0 ? 0 : 1;
+                    const uint32_t* src = a.stream[pi];
+                    for (int c = 0; c < a.nchunks[pi]; ++c, ++cc) {
+                        const uint32_t buf = cc % kRingBufs, use = cc / kRingBufs;
+                        if (use > 0) mbar_wait(empty + buf, (use - 1) & 1);
+                        mbar_expect_tx(full + buf, kChunkBytes);
+                        bulk_g2s(ring + buf * kChunkWords, src + static_cast<size_t>(c) * kChunkWords,
+                                 kChunkBytes, full + buf);
+                    }
+                }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps ----------------
+    V_t* V = reinterpret_cast<V_t*>(smem_raw + kSmallHeaderBytes + per_sys * warp);
     double* Rs = reinterpret_cast<double*>(V + a.n_slots);
-    const int lane = threadIdx.x;
     const V_t* Ax = static_cast<const V_t*>(a.Ax);
     const V_t* B = static_cast<const V_t*>(a.b);
     V_t* Xo = static_cast<V_t*>(a.x);
     V_t* Vst = static_cast<V_t*>(a.Vstore);
-    const int n = a.n, rc = a.rc, r = a.r;
+    uint32_t cc = 0;
 
-    for (int m = blockIdx.x; m < a.L; m += gridDim.x) {
-        const int sm = a.sysidx ? a.sysidx[m] : m;
+    for (int rd = 0; rd < rounds; ++rd) {
+        const int m = rd * per_round + blockIdx.x * W + warp;
+        const bool active = m < a.L;
+        const int sm = (active && a.sysidx) ? a.sysidx[m] : m;
         bool bad = false;
         double gmax = 0.0;
-        if (a.flags & SF_FACTOR) {
-            for (int s = lane; s < a.n_val; s += 32) S::st(V + s, S::zero());
-            __syncwarp();
-            const V_t* Am = Ax + (long long)m * a.ax_stride;
-            for (int e = lane; e < a.nz; e += 32) {
-                const int d = __ldg(a.coo_dst + e);
-                if (d >= 0) S::st(V + d, Am[e]);
-            }
-            __syncwarp();
-            // max-abs row scaling (KLU scale = 2): Rs in original row order
-            for (int i = lane; i < n; i += 32) {
-                const int pb = __ldg(a.rs_ptr + i), pe = __ldg(a.rs_ptr + i + 1);
-                double mx = 0.0;
-                for (int p = pb; p < pe; ++p) mx = fmax(mx, S::mag(S::ld(V + __ldg(a.rs_slot + p))));
-                if (mx == 0.0) mx = 1.0;
-                Rs[i] = mx;
-                for (int p = pb; p < pe; ++p) {
-                    V_t* q = V + __ldg(a.rs_slot + p);
-                    S::st(q, S::rdiv(S::ld(q), mx));
+        if (active) {
+            if (a.flags & SF_FACTOR) {
+                for (int s = lane; s < a.n_val; s += 32) S::st(V + s, S::zero());
+                __syncwarp();
+                const V_t* Am = Ax + (long long)m * a.ax_stride;
+                for (int e = lane; e < a.nz; e += 32) {
+                    const int d = __ldg(a.coo_dst + e);
+                    if (d >= 0) S::st(V + d, Am[e]);
                 }
+                __syncwarp();
+                // max-abs row scaling (KLU scale = 2): Rs in original row order
+                for (int i = lane; i < n; i += 32) {
+                    const int pb = __ldg(a.rs_ptr + i), pe = __ldg(a.rs_ptr + i + 1);
+                    double mx = 0.0;
+                    for (int p = pb; p < pe; ++p) mx = fmax(mx, S::mag(S::ld(V + __ldg(a.rs_slot + p))));
+                    if (mx == 0.0) mx = 1.0;
+                    Rs[i] = mx;
+                    for (int p = pb; p < pe; ++p) {
+                        V_t* q = V + __ldg(a.rs_slot + p);
+                        S::st(q, S::rdiv(S::ld(q), mx));
+                    }
+                }
+            } else if (a.flags & SF_LOAD_NUMERIC) {
+                const V_t* src = Vst + (long long)sm * a.n_val;
+                for (int s = lane; s < a.n_val; s += 32) S::st(V + s, src[s]);
+                const double* rsrc = a.Rsstore + (long long)sm * n;
+                for (int i = lane; i < n; i += 32) Rs[i] = rsrc[i];
             }
-        } else if (a.flags & SF_LOAD_NUMERIC) {
-            const V_t* src = Vst + (long long)sm * a.n_val;
-            for (int s = lane; s < a.n_val; s += 32) S::st(V + s, src[s]);
-            const double* rsrc = a.Rsstore + (long long)sm * n;
-            for (int i = lane; i < n; i += 32) Rs[i] = rsrc[i];
+            if (lane == 0) S::st(V + a.zero_slot, S::zero());
+            __syncwarp();
         }
-        if (lane == 0) S::st(V + a.zero_slot, S::zero());
-        __syncwarp();
 
-        const int nchunk = (a.flags & SF_SOLVE) ? (r + rc - 1) / rc : 1;
-        for (int ch = 0; ch < nchunk; ++ch) {
+        for (int ch = 0; ch < nrhs_chunks; ++ch) {
             const int c0 = ch * rc;
-            if (a.flags & SF_SOLVE) {
+            if (active && (a.flags & SF_SOLVE)) {
                 const V_t* Bm = B + (long long)m * a.b_stride;
                 for (int idx = lane; idx < n * rc; idx += 32) {
                     const int k = idx / rc, c = c0 + idx - k * rc;
@@ -241,10 +313,27 @@ __global__ void __launch_bounds__(32) small_kernel(const SmallArgs a) {
                 }
                 __syncwarp();
             }
+            // ---- interpret the program, chunk by chunk, out of the ring ----
             const int pi = ch == 0 ? 0 : 1;
-            run_program<T>(V, a.ctrl[pi], a.stream[pi], a.nbatch[pi], lane, bad, gmax);
+            for (int c = 0; c < a.nchunks[pi]; ++c, ++cc) {
+                const uint32_t buf = cc % kRingBufs, use = cc / kRingBufs;
+                mbar_wait(full + buf, use & 1);
+                const uint32_t* base = ring + buf * kChunkWords;
+                if (active) {
+                    const uint32_t dir = base[lane];
+                    int pos = 1;
+                    for (int i = 0; i < 32; ++i) {
+                        const uint32_t cw = __shfl_sync(0xffffffffu, dir, i);
+                        if (!cw) break;
+                        run_batch<T>(V, base + pos * 32 + lane, cw, a.zero_word, bad, gmax);
+                        pos += 1 + (cw & 0xFF);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + buf);
+            }
             __syncwarp();
-            if (a.flags & SF_SOLVE) {
+            if (active && (a.flags & SF_SOLVE)) {
                 V_t* Xm = Xo + (long long)m * n * r;
                 for (int idx = lane; idx < n * rc; idx += 32) {
                     const int k = idx / rc, c = c0 + idx - k * rc;
@@ -257,20 +346,22 @@ __global__ void __launch_bounds__(32) small_kernel(const SmallArgs a) {
                 }
             }
         }
-        if (a.flags & SF_STORE_NUMERIC) {
-            V_t* dst = Vst + (long long)sm * a.n_val;
-            for (int s = lane; s < a.n_val; s += 32) dst[s] = S::ld(V + s);
-            double* rdst = a.Rsstore + (long long)sm * n;
-            for (int i = lane; i < n; i += 32) rdst[i] = Rs[i];
-        }
-        if (a.flags & SF_FACTOR) {
-            const bool anybad = __any_sync(0xffffffffu, bad);
-            for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-            if (lane == 0) {
-                int st = anybad ? 1 : 0;
-                if (a.pattern_bad && *a.pattern_bad) st = -3;
-                if (a.status) a.status[m] = st;
-                if (a.growth) a.growth[m] = sqrt(gmax);
+        if (active) {
+            if (a.flags & SF_STORE_NUMERIC) {
+                V_t* dst = Vst + (long long)sm * a.n_val;
+                for (int s = lane; s < a.n_val; s += 32) dst[s] = S::ld(V + s);
+                double* rdst = a.Rsstore + (long long)sm * n;
+                for (int i = lane; i < n; i += 32) rdst[i] = Rs[i];
+            }
+            if (a.flags & SF_FACTOR) {
+                const bool anybad = __any_sync(0xffffffffu, bad);
+                for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+                if (lane == 0) {
+                    int st = anybad ? 1 : 0;
+                    if (a.pattern_bad && *a.pattern_bad) st = -3;
+                    if (a.status) a.status[m] = st;
+                    if (a.growth) a.growth[m] = sqrt(gmax);
+                }
             }
         }
         __syncwarp();

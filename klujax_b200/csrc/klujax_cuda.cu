@@ -67,8 +67,9 @@ struct DevBuf {
 };
 
 struct SmallProg {
-    DevBuf ctrl, stream;
-    int nbatch = 0, n_slots = 0, zero_slot = 0, nlevels = 0;
+    DevBuf stream;
+    int nchunks = 0, nbatch = 0, n_slots = 0, zero_slot = 0, nlevels = 0;
+    uint32_t zero_word = 0;
     int64_t n_mac = 0;
 };
 
@@ -81,7 +82,7 @@ struct Seeded {
     DevBuf d_colptr, d_srow, d_sslot, d_rs_ptr, d_rs_slot, d_pnum, d_q;
     std::map<std::pair<int, int>, std::unique_ptr<SmallProg>> small;
     std::map<std::pair<int, int>, std::unique_ptr<LevelProg>> level;
-    int64_t info_levels = 0, info_mac = 0;
+    int64_t info_levels = 0, info_mac = 0, info_nbatch = 0, info_stream_words = 0;
 };
 
 struct Symbolic {
@@ -139,10 +140,12 @@ static int seed_from_csc_values(Symbolic* S, int cx, const T* csc_values) {
     PackedProgram pp;
     const size_t vsz = cx ? 16 : 8;
     sd.regime = 1;
-    if (static_cast<size_t>(sd.lay.n_val + sd.lay.n + 1) * vsz + sd.lay.n * 8ull <= kMaxDynSmem &&
+    if (static_cast<size_t>(sd.lay.n_val + sd.lay.n + 1) * vsz + sd.lay.n * 8ull + 16 <= kMaxDynSmem - kSmallHeaderBytes &&
         sd.lay.n_val + sd.lay.n + 1 <= 16383) {
-        build_program(S->ord, sd.piv, sd.lay, PM_FACTOR_SOLVE, 1, tp);
+        build_program(S->ord, sd.piv, sd.lay, PM_FACTOR_SOLVE, 1, tp, 1);
         if (pack_program(sd.lay, tp, pp)) sd.regime = 0;
+        sd.info_nbatch = pp.nbatch;
+        sd.info_stream_words = static_cast<int64_t>(pp.stream.size());
         sd.info_levels = tp.nlevels;
     }
     if (const char* force = std::getenv("KLUJAX_CUDA_FORCE_REGIME")) sd.regime = std::atoi(force) ? 1 : 0;
@@ -232,12 +235,15 @@ static int get_small_prog(Symbolic* S, int cx, int mode, int rc, SmallProg** out
     if (it == sd.small.end()) {
         TaskProgram tp;
         PackedProgram pp;
-        build_program(S->ord, sd.piv, sd.lay, mode, rc, tp);
+        int split = 1;
+        if (const char* e = std::getenv("KLUJAX_CUDA_SPLIT")) split = std::atoi(e);
+        build_program(S->ord, sd.piv, sd.lay, mode, rc, tp, split);
         if (!pack_program(sd.lay, tp, pp)) return fail(KLU_TOO_LARGE, "program does not fit the shared-memory regime");
         auto sp = std::make_unique<SmallProg>();
-        CUDA_OK(sp->ctrl.upload(pp.ctrl));
         CUDA_OK(sp->stream.upload(pp.stream));
+        sp->nchunks = pp.nchunks;
         sp->nbatch = pp.nbatch;
+        sp->zero_word = pp.zero_word;
         sp->n_slots = pp.n_slots;
         sp->zero_slot = pp.zero_slot;
         sp->nlevels = tp.nlevels;
@@ -298,7 +304,7 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
         // widest right-hand-side chunk that still fits the slot fields / shared memory
         for (rc = std::min(op.r, 4); rc >= 1; --rc) {
             const size_t slots = static_cast<size_t>(sd.lay.n_val) + static_cast<size_t>(n) * rc + 1;
-            if (slots <= 16383 && slots * vsz + n * 8ull <= kMaxDynSmem) break;
+            if (slots <= 16383 && slots * vsz + n * 8ull + 16 <= kMaxDynSmem - kSmallHeaderBytes) break;
         }
         if (rc < 1) return fail(KLU_TOO_LARGE, "system does not fit the shared-memory regime");
     }
@@ -310,13 +316,12 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     }
     SmallArgs a;
     std::memset(&a, 0, sizeof(a));
-    a.ctrl[0] = p0->ctrl.as<uint32_t>();
     a.stream[0] = p0->stream.as<uint32_t>();
-    a.nbatch[0] = p0->nbatch;
+    a.nchunks[0] = p0->nchunks;
+    a.zero_word = p0->zero_word;
     if (p1) {
-        a.ctrl[1] = p1->ctrl.as<uint32_t>();
         a.stream[1] = p1->stream.as<uint32_t>();
-        a.nbatch[1] = p1->nbatch;
+        a.nchunks[1] = p1->nchunks;
     }
     a.n = n;
     a.n_val = sd.lay.n_val;
@@ -347,14 +352,25 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     a.status = op.status;
     a.growth = op.growth;
     a.L = op.L;
-    const size_t smem = static_cast<size_t>(a.n_slots) * vsz + n * 8ull;
+    // CTA = W systems (one consumer warp each) + the producer warp + the schedule ring.
+    // W: as many value arrays as fit next to the ring, but enough CTAs to cover the SMs.
+    const size_t per_sys = (static_cast<size_t>(a.n_slots) * vsz + n * 8ull + 15) & ~size_t(15);
+    int W = static_cast<int>(std::min<size_t>(16, (kMaxDynSmem - kSmallHeaderBytes) / per_sys));
+    if (W < 1) return fail(KLU_TOO_LARGE, "system does not fit the shared-memory regime");
+    const int sms = num_sms();
+    while (W > 1 && (op.L + W - 1) / W < sms) --W;  // small batches: spread over all SMs first
+    if (const char* fw = std::getenv("KLUJAX_CUDA_SMALL_W")) W = std::max(1, std::min(W, std::atoi(fw)));
+    a.W = W;
+    const size_t smem = kSmallHeaderBytes + per_sys * W;
+    const int threads = 32 * (W + 1);
     auto kern = small_kernel<T>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int occ = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ < 1) return fail(KLU_TOO_LARGE, "shared-memory regime: zero occupancy");
-    const int grid = static_cast<int>(std::min<long long>(op.L, static_cast<long long>(occ) * num_sms()));
-    kern<<<grid, 32, smem, op.st>>>(a);
+    const long long ctas = (op.L + W - 1) / W;
+    const int grid = static_cast<int>(std::min<long long>(ctas, static_cast<long long>(occ) * sms));
+    kern<<<grid, threads, smem, op.st>>>(a);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -556,6 +572,8 @@ int klujax_cuda_symbolic_info(uint64_t symbolic, int is_complex, int64_t* o) {
     o[9] = sd.ok ? sd.info_levels : -1;
     o[10] = sd.ok ? sd.info_mac : -1;
     o[11] = sd.ok ? sd.piv.noffdiag : -1;
+    o[12] = sd.ok ? sd.info_nbatch : -1;
+    o[13] = sd.ok ? sd.info_stream_words : -1;
     return 0;
 }
 

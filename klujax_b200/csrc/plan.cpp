@@ -102,42 +102,82 @@ void build_layout(const CscPattern& A, const Ordering& ord, const PivotPlan& piv
 namespace {
 
 // Assigns levels while tasks are appended in a valid sequential order.
+//
+// split = false: one task per destination, at the level where its last operand is final
+//                (pure "dot" form).
+// split = true : the multiply-adds of a destination are applied as soon as their operands
+//                are final: one partial task per (destination, level), the last one carrying
+//                the finishing operation.  Same critical path, but the work of a long dot
+//                product is spread over the levels before it and chains (dense trailing
+//                blocks, back substitution) become one short update per level instead of
+//                one long reduction per level.
 struct Leveler {
     std::vector<int> val_level, read_level;
     TaskProgram& prog;
-    Leveler(int nidx, TaskProgram& p) : val_level(nidx, 0), read_level(nidx, 0), prog(p) {}
-    void add(uint8_t kind, int out, int div, const std::vector<std::pair<int, int>>& pairs) {
+    bool split;
+    std::vector<std::pair<int, int>> order;  // (ready level, pair index)
+    Leveler(int nidx, TaskProgram& p, bool split_) : val_level(nidx, 0), read_level(nidx, 0), prog(p), split(split_) {}
+
+    void emit(uint8_t kind, int out, int div, int lvl, const std::vector<std::pair<int, int>>& pairs,
+              int ob, int oe) {
         Task t;
         t.kind = kind;
         t.out = out;
         t.div = div;
+        t.level = lvl;
         t.pbeg = static_cast<int>(prog.pa.size());
-        t.plen = static_cast<int>(pairs.size());
-        int lvl = std::max(val_level[out], read_level[out]);
-        if (div >= 0) lvl = std::max(lvl, val_level[div]);
-        for (const auto& pr : pairs) {
-            lvl = std::max(lvl, std::max(val_level[pr.first], val_level[pr.second]));
+        t.plen = oe - ob;
+        for (int q = ob; q < oe; ++q) {
+            const auto& pr = pairs[order[q].second];
             prog.pa.push_back(pr.first);
             prog.pb.push_back(pr.second);
-        }
-        lvl += 1;
-        t.level = lvl;
-        if (div >= 0) read_level[div] = std::max(read_level[div], lvl);
-        for (const auto& pr : pairs) {
             read_level[pr.first] = std::max(read_level[pr.first], lvl);
             read_level[pr.second] = std::max(read_level[pr.second], lvl);
         }
-        val_level[out] = lvl;
-        read_level[out] = 0;
+        if (div >= 0) read_level[div] = std::max(read_level[div], lvl);
         prog.n_mac += t.plen;
         prog.tasks.push_back(t);
+    }
+
+    void add(uint8_t kind, int out, int div, const std::vector<std::pair<int, int>>& pairs) {
+        // nothing may touch `out` before its previous version is final and has been read
+        const int base = std::max(val_level[out], read_level[out]) + 1;
+        const int np = static_cast<int>(pairs.size());
+        order.resize(np);
+        int last = base;
+        for (int q = 0; q < np; ++q) {
+            int lp = std::max(val_level[pairs[q].first], val_level[pairs[q].second]) + 1;
+            lp = std::max(lp, base);
+            order[q] = {lp, q};
+            last = std::max(last, lp);
+        }
+        if (div >= 0) last = std::max(last, val_level[div] + 1);
+        if (!split) {
+            for (int q = 0; q < np; ++q) order[q].first = last;
+        } else {
+            std::stable_sort(order.begin(), order.end(),
+                             [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first < y.first; });
+        }
+        int ob = 0;
+        while (ob < np) {
+            int oe = ob;
+            while (oe < np && order[oe].first == order[ob].first) ++oe;
+            if (oe == np) break;  // the last group carries the finishing operation
+            emit(TK_SUB, out, -1, order[ob].first, pairs, ob, oe);
+            ob = oe;
+        }
+        // last group (possibly empty) + finish; it may have to wait for the pivot
+        if (np == 0 && kind == TK_SUB) return;  // V[out] -= nothing
+        emit(kind, out, div, last, pairs, ob, np);
+        val_level[out] = last;
+        read_level[out] = 0;
     }
 };
 
 }  // namespace
 
 void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
-                   int rc, TaskProgram& prog) {
+                   int rc, TaskProgram& prog, int split) {
     const int n = lay.n;
     prog = TaskProgram();
     prog.mode = mode;
@@ -146,7 +186,9 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
     const bool do_solve = (mode == PM_FACTOR_SOLVE || mode == PM_SOLVE);
     const bool do_tsolve = (mode == PM_FACTOR_TSOLVE || mode == PM_TSOLVE);
     const int nx = (do_solve || do_tsolve) ? n * rc : 0;
-    Leveler lv(lay.n_val + nx, prog);
+    // split: 0 = dot form everywhere, 1 = as-soon-as-possible updates in the triangular
+    // solves only, 2 = everywhere
+    Leveler lv(lay.n_val + nx, prog, split >= 2);
     const std::vector<int> k1of = block_of_column(ord);
     auto xs = [&](int k, int c) { return lay.n_val + k * rc + c; };
     std::vector<std::pair<int, int>> pairs;
@@ -186,6 +228,7 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
         }
     }
 
+    lv.split = split >= 1;
     if (do_solve) {
         // row-wise views of L, U and the off-diagonal blocks
         std::vector<std::vector<std::pair<int, int>>> lrow(n), urow(n), offrow(n);
@@ -276,32 +319,55 @@ bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram&
     out.n_slots = out.zero_slot + 1;
     if (out.n_slots > 16383) return false;  // 14-bit slot fields, 0x3FFF = no pivot operand
     const uint32_t zero_word = (static_cast<uint32_t>(out.zero_slot) << 16) | out.zero_slot;
-    auto batch_cost = [](int p, int lg) { return 16 * ((p + (1 << lg) - 1) >> lg) + 33 * lg + 60; };
+    out.zero_word = zero_word;
+    constexpr int CH = kChunkLines, MAXRUN = kChunkLines - 2;
+    int line = CH, nbatch_in_chunk = 0;  // forces a first chunk
+    size_t chunk_base = 0;
+    auto open_chunk = [&]() {
+        chunk_base = out.stream.size();
+        out.stream.resize(chunk_base + static_cast<size_t>(CH) * 32, zero_word);
+        for (int lane = 0; lane < 32; ++lane) out.stream[chunk_base + lane] = 0;  // empty directory
+        line = 1;
+        nbatch_in_chunk = 0;
+        out.nchunks++;
+    };
+    std::vector<long> f;
+    std::vector<int> choice;
     for (int l = 0; l < prog.nlevels; ++l) {
-        const int tb = prog.level_ptr[l], te = prog.level_ptr[l + 1];
-        // pick one lane-group width for the level: g lanes share one dot product
-        int best_lg = 0;
-        long best_cost = -1;
-        for (int lg = 0; lg <= 5; ++lg) {
-            const int per = 32 >> lg;
-            long cost = 0;
-            for (int t = tb; t < te; t += per) cost += batch_cost(prog.tasks[t].plen, lg);
-            if (best_cost < 0 || cost < best_cost) {
-                best_cost = cost;
-                best_lg = lg;
+        const int tb = prog.level_ptr[l], te = prog.level_ptr[l + 1], T = te - tb;
+        // Tasks of a level are sorted by dot length (longest first).  Dynamic program over
+        // that order: a batch takes the next 32/g tasks and gives each g lanes (run =
+        // ceil(longest/g) operand lines + one header line + a log2(g)-step shuffle reduce).
+        f.assign(T + 1, 0);
+        choice.assign(T, 0);
+        for (int i = T - 1; i >= 0; --i) {
+            long best = -1;
+            int best_lg = -1;
+            for (int lg = 0; lg <= 5; ++lg) {
+                const int g = 1 << lg, cnt = std::min(32 >> lg, T - i);
+                const int run = (prog.tasks[tb + i].plen + g - 1) / g;
+                if (run > MAXRUN) continue;
+                const long c = run + 2 + lg + f[i + cnt];
+                if (best < 0 || c < best) {
+                    best = c;
+                    best_lg = lg;
+                }
             }
+            if (best_lg < 0) return false;  // a dot product too long for one chunk
+            f[i] = best;
+            choice[i] = best_lg;
         }
-        const int g = 1 << best_lg, per = 32 >> best_lg;
-        for (int t0 = tb; t0 < te; t0 += per) {
-            const int t1 = std::min(te, t0 + per);
-            const int run = (prog.tasks[t0].plen + g - 1) / g;  // tasks are sorted by plen desc
-            if (run > 4095) return false;
+        for (int i = 0; i < T;) {
+            const int lg = choice[i], g = 1 << lg, cnt = std::min(32 >> lg, T - i);
+            const int t0 = tb + i, t1 = t0 + cnt;
+            const int run = (prog.tasks[t0].plen + g - 1) / g;
+            if (line + 1 + run > CH || nbatch_in_chunk == 32) open_chunk();
             const bool last = (t1 == te);
-            out.ctrl.push_back(static_cast<uint32_t>(run) | (static_cast<uint32_t>(best_lg) << 12) |
-                               (last ? (1u << 15) : 0u));
-            const size_t base = out.stream.size();
-            out.stream.resize(base + 32 * static_cast<size_t>(1 + run), zero_word);
-            for (int lane = 0; lane < 32; ++lane) out.stream[base + lane] = 0;  // TK_NOP
+            out.stream[chunk_base + nbatch_in_chunk] = 0x80000000u | static_cast<uint32_t>(run) |
+                                                       (static_cast<uint32_t>(lg) << 8) |
+                                                       (last ? (1u << 11) : 0u);
+            const size_t base = chunk_base + static_cast<size_t>(line) * 32;
+            for (int lane = 0; lane < 32; ++lane) out.stream[base + lane] = 0;  // TK_NOP headers
             for (int t = t0; t < t1; ++t) {
                 const Task& tk = prog.tasks[t];
                 const int lead = (t - t0) * g;
@@ -315,7 +381,11 @@ bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram&
                         static_cast<uint32_t>(prog.pb[tk.pbeg + q]);
                 }
             }
+            line += 1 + run;
+            nbatch_in_chunk++;
             out.nbatch++;
+            out.lines_used += 1 + run;
+            i += cnt;
         }
     }
     return true;

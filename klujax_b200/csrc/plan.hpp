@@ -73,14 +73,20 @@ struct TaskProgram {
 
 void build_layout(const CscPattern& A, const Ordering& ord, const PivotPlan& piv, SlotLayout& lay);
 void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
-                   int rc, TaskProgram& prog);
+                   int rc, TaskProgram& prog, int split = 0);
 
-// Packed instruction stream of the shared-memory (small-matrix) regime: one warp
-// interprets it per system.  See kernels_small.cu for the decoding.
+// Packed instruction stream of the shared-memory (small-matrix) regime.  The stream is cut
+// into chunks of kChunkLines lines of 32 words (one word per lane); a chunk is what one TMA
+// bulk copy brings into the shared-memory ring.  Line 0 of a chunk is its directory: word i
+// describes batch i of the chunk (0 = end): bit31 valid | run (bits 0-7) | log2 g (bits 8-10)
+// | level-ends-here (bit 11).  A batch is one header line (per lane: kind<<28 | out<<14 |
+// pivot slot) followed by `run` operand lines (per lane: a<<16 | b, zero_word = idle lane).
+constexpr int kChunkLines = 32;
 struct PackedProgram {
-    std::vector<uint32_t> ctrl;    // per batch: run | log2g<<12 | sync<<15
-    std::vector<uint32_t> stream;  // per batch: 32 header words + run*32 operand words
-    int nbatch = 0, zero_slot = 0, n_slots = 0;  // n_slots includes X and the zero slot
+    std::vector<uint32_t> stream;  // nchunks * kChunkLines * 32 words
+    int nchunks = 0, nbatch = 0, zero_slot = 0, n_slots = 0;  // n_slots includes X and the zero slot
+    uint32_t zero_word = 0;
+    int64_t lines_used = 0;
 };
 bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out);
 
