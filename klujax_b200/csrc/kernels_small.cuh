@@ -39,6 +39,16 @@ struct Sc<double> {
     __device__ static __forceinline__ V shfl_down(V a, int o, int w) {
         return __shfl_down_sync(0xffffffffu, a, o, w);
     }
+    __device__ static __forceinline__ V one() { return 1.0; }
+    // split accumulators: independent FMA chains, combined once per batch
+    struct Acc {
+        double p, q;
+    };
+    __device__ static __forceinline__ Acc acc0() { return {0.0, 0.0}; }
+    __device__ static __forceinline__ void mac(Acc& c, V a, V b, int which) {
+        if (which & 1) c.q = fma(a, b, c.q); else c.p = fma(a, b, c.p);
+    }
+    __device__ static __forceinline__ V fold(const Acc& c) { return c.p + c.q; }
 };
 template <>
 struct Sc<zc> {
@@ -76,6 +86,19 @@ struct Sc<zc> {
         return make_double2(__shfl_down_sync(0xffffffffu, a.x, o, w),
                             __shfl_down_sync(0xffffffffu, a.y, o, w));
     }
+    __device__ static __forceinline__ V one() { return make_double2(1.0, 0.0); }
+    // four independent FMA chains (xx, yy, xy, yx), combined once per batch
+    struct Acc {
+        double xx, yy, xy, yx;
+    };
+    __device__ static __forceinline__ Acc acc0() { return {0.0, 0.0, 0.0, 0.0}; }
+    __device__ static __forceinline__ void mac(Acc& c, V a, V b, int) {
+        c.xx = fma(a.x, b.x, c.xx);
+        c.yy = fma(a.y, b.y, c.yy);
+        c.xy = fma(a.x, b.y, c.xy);
+        c.yx = fma(a.y, b.x, c.yx);
+    }
+    __device__ static __forceinline__ V fold(const Acc& c) { return make_double2(c.xx - c.yy, c.xy + c.yx); }
 };
 
 enum SmallFlags : int {
@@ -92,7 +115,6 @@ struct SmallArgs {
     // [1] further right-hand-side chunks (solve only)
     const uint32_t* stream[2];
     int nchunks[2];
-    uint32_t zero_word;
     int W;                   // systems (= consumer warps) per CTA
     int n, n_val, n_slots, zero_slot, rc, nz, flags;
     const int* coo_dst;      // [nz] slot of each COO entry of this call, -1 = not in pattern
@@ -113,10 +135,11 @@ struct SmallArgs {
     int* status;
     double* growth;
     int L;
+    unsigned long long* prof;  // optional [8] cycle counters (KLUJAX_CUDA_PROFILE=1)
+    int dbg;                   // KLUJAX_CUDA_DBG bisection flags (wrong results!), 0 in production
 };
 
 constexpr int kRingBufs = 3;                                   // chunks in flight per CTA
-constexpr int kChunkWords = kChunkLines * 32;
 constexpr int kChunkBytes = kChunkWords * 4;
 constexpr int kRingBytes = kRingBufs * kChunkBytes;
 constexpr int kSmallHeaderBytes = kRingBytes + 128;            // ring + mbarriers
@@ -156,49 +179,93 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
-// One batch: `run` operand lines, an optional lane-group reduction, then every leading
-// lane finishes its task.  `line` points at the batch header in the shared-memory ring.
+// Operand fetch: slot fields of the stream words are pre-multiplied by 16.
 template <typename T>
-__device__ __forceinline__ void run_batch(typename Sc<T>::V* __restrict__ V,
-                                          const uint32_t* __restrict__ line, uint32_t cw,
-                                          uint32_t zero_word, bool& bad, double& gmax) {
+__device__ __forceinline__ typename Sc<T>::V* slot_hi(unsigned char* Vb, uint32_t w) {
+    constexpr int SH = (sizeof(typename Sc<T>::V) == 16) ? 0 : 1;
+    return reinterpret_cast<typename Sc<T>::V*>(Vb + ((w >> (14 + SH)) & (0x3FFF0u >> SH)));
+}
+template <typename T>
+__device__ __forceinline__ typename Sc<T>::V* slot_lo(unsigned char* Vb, uint32_t w) {
+    constexpr int SH = (sizeof(typename Sc<T>::V) == 16) ? 0 : 1;
+    return reinterpret_cast<typename Sc<T>::V*>(Vb + ((w >> SH) & (0x3FFF0u >> SH)));
+}
+
+// Runs every batch of one chunk out of the shared-memory ring.  Per batch and lane:
+// acc = sum a*b over 2*trips operand lines; tree-reduce over g lanes; then
+// V[out] = (V[out] - acc) * V[pivot-or-ONE], or the reciprocal for a batch of pivots.
+// The next batch's control and header words are fetched before the current batch stores.
+template <typename T>
+__device__ __forceinline__ void run_chunk(unsigned char* __restrict__ Vb,
+                                          const uint32_t* __restrict__ p, bool& bad, double& gmax,
+                                          const int dbg) {
     using S = Sc<T>;
     using V_t = typename S::V;
-    const int run = cw & 0xFF, lg = (cw >> 8) & 7;
-    const uint32_t h = line[0];
-    const int kind = h >> 28, out = (h >> 14) & 0x3FFF, dv = h & 0x3FFF;
-    V_t vo = S::zero(), vd = S::zero();
-    if (kind) vo = S::ld(V + out);
-    if (kind >= TK_MUL) vd = S::ld(V + dv);
-    V_t acc0 = S::zero(), acc1 = S::zero();
-    const uint32_t* ops = line + 32;
-    int q = 0;
-    for (; q + 2 <= run; q += 2) {
-        const uint32_t w0 = ops[32 * q], w1 = ops[32 * q + 32];
-        if (w0 != zero_word) S::fma_acc(acc0, S::ld(V + (w0 >> 16)), S::ld(V + (w0 & 0xFFFF)));
-        if (w1 != zero_word) S::fma_acc(acc1, S::ld(V + (w1 >> 16)), S::ld(V + (w1 & 0xFFFF)));
+    uint32_t cw = p[0], h = p[32];
+    while (cw) {
+        int trips = cw & 0xFF;
+        const int type = (cw >> 8) & 0xF;
+        const uint32_t* ops = p + 64;
+        p = ops + trips * 64;
+        const uint32_t ncw = p[0], nh = p[32];
+        V_t* po = slot_hi<T>(Vb, h);
+        const V_t vo = *po;
+        const V_t vd = *slot_lo<T>(Vb, h);
+        typename S::Acc c = S::acc0();
+        do {
+            const uint32_t w0 = ops[0], w1 = ops[32];
+            ops += 64;
+            V_t a0, b0, a1, b1;
+            if (dbg & 1) {  // no operand loads
+                a0 = b0 = a1 = b1 = vo;
+            } else {
+                a0 = *slot_hi<T>(Vb, w0), b0 = *slot_lo<T>(Vb, w0);
+                a1 = *slot_hi<T>(Vb, w1), b1 = *slot_lo<T>(Vb, w1);
+            }
+            if (!(dbg & 2)) {
+                S::mac(c, a0, b0, 0);
+                S::mac(c, a1, b1, 1);
+            } else if (w0 == 0x12345678u) {
+                S::mac(c, a0, b0, 0);
+                S::mac(c, a1, b1, 1);
+            }
+        } while (--trips);
+        V_t acc = S::fold(c);
+#define KB_RED(o) acc = S::add(acc, S::shfl_down(acc, o, 32))
+#define KB_FINISH                                              \
+    {                                                          \
+        const V_t t = S::mul(S::sub(vo, acc), vd);             \
+        gmax = fmax(gmax, (h & 1u) ? S::mag2(t) : 0.0);        \
+        *po = t;                                               \
     }
-    if (q < run) {
-        const uint32_t w0 = ops[32 * q];
-        if (w0 != zero_word) S::fma_acc(acc0, S::ld(V + (w0 >> 16)), S::ld(V + (w0 & 0xFFFF)));
+#define KB_PIVOT                                               \
+    {                                                          \
+        const V_t t = S::sub(vo, acc);                         \
+        if (h & 2u) bad |= S::bad_pivot(t);                    \
+        *po = S::recip(t);                                     \
     }
-    V_t acc = S::add(acc0, acc1);
-    if (lg) {
-        const int g = 1 << lg;
-        for (int o = g >> 1; o > 0; o >>= 1) acc = S::add(acc, S::shfl_down(acc, o, g));
-    }
-    if (kind) {
-        V_t t = S::sub(vo, acc);
-        if (kind == TK_RECIP) {
-            bad |= S::bad_pivot(t);
-            t = S::recip(t);
-        } else if (kind >= TK_MUL) {
-            t = S::mul(t, vd);
-            if (kind == TK_MUL_TRACK) gmax = fmax(gmax, S::mag2(t));
+        // a group leader only ever reads lanes of its own group
+        switch ((dbg & 8) ? 0 : type) {
+            case 0: KB_FINISH break;
+            case 1: KB_RED(1); KB_FINISH break;
+            case 2: KB_RED(2); KB_RED(1); KB_FINISH break;
+            case 3: KB_RED(4); KB_RED(2); KB_RED(1); KB_FINISH break;
+            case 4: KB_RED(8); KB_RED(4); KB_RED(2); KB_RED(1); KB_FINISH break;
+            case 5: KB_RED(16); KB_RED(8); KB_RED(4); KB_RED(2); KB_RED(1); KB_FINISH break;
+            case 6: KB_PIVOT break;
+            case 7: KB_RED(1); KB_PIVOT break;
+            case 8: KB_RED(2); KB_RED(1); KB_PIVOT break;
+            case 9: KB_RED(4); KB_RED(2); KB_RED(1); KB_PIVOT break;
+            case 10: KB_RED(8); KB_RED(4); KB_RED(2); KB_RED(1); KB_PIVOT break;
+            default: KB_RED(16); KB_RED(8); KB_RED(4); KB_RED(2); KB_RED(1); KB_PIVOT break;
         }
-        S::st(V + out, t);
+#undef KB_RED
+#undef KB_FINISH
+#undef KB_PIVOT
+        if (!(dbg & 4)) __syncwarp();
+        cw = ncw;
+        h = nh;
     }
-    if (cw & 0x800u) __syncwarp();
 }
 
 // CTA = W consumer warps (one system each, private value array in shared memory) + one
@@ -206,7 +273,7 @@ __device__ __forceinline__ void run_batch(typename Sc<T>::V* __restrict__ V,
 // bulk copies; full/empty mbarriers pace it.  All consumer warps of a CTA walk the same
 // program, so the schedule is read from L2 once per CTA, not once per system.
 template <typename T>
-__global__ void __launch_bounds__(544) small_kernel(const SmallArgs a) {
+__global__ void __launch_bounds__(544, 1) small_kernel(const SmallArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -258,6 +325,8 @@ __global__ void __launch_bounds__(544) small_kernel(const SmallArgs a) {
     V_t* Xo = static_cast<V_t*>(a.x);
     V_t* Vst = static_cast<V_t*>(a.Vstore);
     uint32_t cc = 0;
+    long long t_load = 0, t_b = 0, t_wait = 0, t_run = 0, t_store = 0, t0 = 0;
+    const bool prof = a.prof != nullptr;
 
     for (int rd = 0; rd < rounds; ++rd) {
         const int m = rd * per_round + blockIdx.x * W + warp;
@@ -265,12 +334,36 @@ __global__ void __launch_bounds__(544) small_kernel(const SmallArgs a) {
         const int sm = (active && a.sysidx) ? a.sysidx[m] : m;
         bool bad = false;
         double gmax = 0.0;
+        if (prof) t0 = clock64();
         if (active) {
             if (a.flags & SF_FACTOR) {
                 for (int s = lane; s < a.n_val; s += 32) S::st(V + s, S::zero());
                 __syncwarp();
                 const V_t* Am = Ax + (long long)m * a.ax_stride;
-                for (int e = lane; e < a.nz; e += 32) {
+                {   // pull the next round's inputs of this warp towards L2 while this system runs
+                    const long long mn = (long long)m + per_round;
+                    if (mn < a.L) {
+                        const char* nx = reinterpret_cast<const char*>(Ax + mn * a.ax_stride);
+                        for (int o = lane * 128; o < a.nz * (int)sizeof(V_t); o += 32 * 128)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+                        if (a.flags & SF_SOLVE) {
+                            const char* nb = reinterpret_cast<const char*>(B + mn * a.b_stride);
+                            for (int o = lane * 128; o < n * r * (int)sizeof(V_t); o += 32 * 128)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
+                        }
+                    }
+                }
+                int e = lane;
+                for (; e + 96 < a.nz; e += 128) {
+                    const int d0 = __ldg(a.coo_dst + e), d1 = __ldg(a.coo_dst + e + 32),
+                              d2 = __ldg(a.coo_dst + e + 64), d3 = __ldg(a.coo_dst + e + 96);
+                    const V_t v0 = Am[e], v1 = Am[e + 32], v2 = Am[e + 64], v3 = Am[e + 96];
+                    if (d0 >= 0) S::st(V + d0, v0);
+                    if (d1 >= 0) S::st(V + d1, v1);
+                    if (d2 >= 0) S::st(V + d2, v2);
+                    if (d3 >= 0) S::st(V + d3, v3);
+                }
+                for (; e < a.nz; e += 32) {
                     const int d = __ldg(a.coo_dst + e);
                     if (d >= 0) S::st(V + d, Am[e]);
                 }
@@ -293,9 +386,14 @@ __global__ void __launch_bounds__(544) small_kernel(const SmallArgs a) {
                 const double* rsrc = a.Rsstore + (long long)sm * n;
                 for (int i = lane; i < n; i += 32) Rs[i] = rsrc[i];
             }
-            if (lane == 0) S::st(V + a.zero_slot, S::zero());
-            __syncwarp();
         }
+        if (lane == 0) {
+            S::st(V + a.zero_slot, S::zero());
+            S::st(V + a.zero_slot + 1, S::one());
+            S::st(V + a.zero_slot + 2, S::zero());
+        }
+        __syncwarp();
+        if (prof) { const long long t1 = clock64(); t_load += t1 - t0; t0 = t1; }
 
         for (int ch = 0; ch < nrhs_chunks; ++ch) {
             const int c0 = ch * rc;
@@ -313,24 +411,19 @@ __global__ void __launch_bounds__(544) small_kernel(const SmallArgs a) {
                 }
                 __syncwarp();
             }
+            if (prof) { const long long t1 = clock64(); t_b += t1 - t0; t0 = t1; }
             // ---- interpret the program, chunk by chunk, out of the ring ----
             const int pi = ch == 0 ? 0 : 1;
             for (int c = 0; c < a.nchunks[pi]; ++c, ++cc) {
                 const uint32_t buf = cc % kRingBufs, use = cc / kRingBufs;
                 mbar_wait(full + buf, use & 1);
+                if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
                 const uint32_t* base = ring + buf * kChunkWords;
-                if (active) {
-                    const uint32_t dir = base[lane];
-                    int pos = 1;
-                    for (int i = 0; i < 32; ++i) {
-                        const uint32_t cw = __shfl_sync(0xffffffffu, dir, i);
-                        if (!cw) break;
-                        run_batch<T>(V, base + pos * 32 + lane, cw, a.zero_word, bad, gmax);
-                        pos += 1 + (cw & 0xFF);
-                    }
-                }
+                // every consumer warp runs the program (idle ones on scratch values)
+                run_chunk<T>(reinterpret_cast<unsigned char*>(V), base + lane, bad, gmax, a.dbg);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + buf);
+                if (prof) { const long long t1 = clock64(); t_run += t1 - t0; t0 = t1; }
             }
             __syncwarp();
             if (active && (a.flags & SF_SOLVE)) {
@@ -365,6 +458,15 @@ __global__ void __launch_bounds__(544) small_kernel(const SmallArgs a) {
             }
         }
         __syncwarp();
+        if (prof) { const long long t1 = clock64(); t_store += t1 - t0; t0 = t1; }
+    }
+    if (prof && lane == 0) {
+        atomicAdd(a.prof + 0, (unsigned long long)t_load);
+        atomicAdd(a.prof + 1, (unsigned long long)t_b);
+        atomicAdd(a.prof + 2, (unsigned long long)t_wait);
+        atomicAdd(a.prof + 3, (unsigned long long)t_run);
+        atomicAdd(a.prof + 4, (unsigned long long)t_store);
+        atomicAdd(a.prof + 5, 1ull);
     }
 }
 

@@ -69,7 +69,6 @@ struct DevBuf {
 struct SmallProg {
     DevBuf stream;
     int nchunks = 0, nbatch = 0, n_slots = 0, zero_slot = 0, nlevels = 0;
-    uint32_t zero_word = 0;
     int64_t n_mac = 0;
 };
 
@@ -140,8 +139,8 @@ static int seed_from_csc_values(Symbolic* S, int cx, const T* csc_values) {
     PackedProgram pp;
     const size_t vsz = cx ? 16 : 8;
     sd.regime = 1;
-    if (static_cast<size_t>(sd.lay.n_val + sd.lay.n + 1) * vsz + sd.lay.n * 8ull + 16 <= kMaxDynSmem - kSmallHeaderBytes &&
-        sd.lay.n_val + sd.lay.n + 1 <= 16383) {
+    if (static_cast<size_t>(sd.lay.n_val + sd.lay.n + 3) * vsz + sd.lay.n * 8ull + 16 <= kMaxDynSmem - kSmallHeaderBytes &&
+        sd.lay.n_val + sd.lay.n + 3 <= 16383) {
         build_program(S->ord, sd.piv, sd.lay, PM_FACTOR_SOLVE, 1, tp, 1);
         if (pack_program(sd.lay, tp, pp)) sd.regime = 0;
         sd.info_nbatch = pp.nbatch;
@@ -243,7 +242,6 @@ static int get_small_prog(Symbolic* S, int cx, int mode, int rc, SmallProg** out
         CUDA_OK(sp->stream.upload(pp.stream));
         sp->nchunks = pp.nchunks;
         sp->nbatch = pp.nbatch;
-        sp->zero_word = pp.zero_word;
         sp->n_slots = pp.n_slots;
         sp->zero_slot = pp.zero_slot;
         sp->nlevels = tp.nlevels;
@@ -303,7 +301,7 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     if (solve) {
         // widest right-hand-side chunk that still fits the slot fields / shared memory
         for (rc = std::min(op.r, 4); rc >= 1; --rc) {
-            const size_t slots = static_cast<size_t>(sd.lay.n_val) + static_cast<size_t>(n) * rc + 1;
+            const size_t slots = static_cast<size_t>(sd.lay.n_val) + static_cast<size_t>(n) * rc + 3;
             if (slots <= 16383 && slots * vsz + n * 8ull + 16 <= kMaxDynSmem - kSmallHeaderBytes) break;
         }
         if (rc < 1) return fail(KLU_TOO_LARGE, "system does not fit the shared-memory regime");
@@ -318,7 +316,6 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     std::memset(&a, 0, sizeof(a));
     a.stream[0] = p0->stream.as<uint32_t>();
     a.nchunks[0] = p0->nchunks;
-    a.zero_word = p0->zero_word;
     if (p1) {
         a.stream[1] = p1->stream.as<uint32_t>();
         a.nchunks[1] = p1->nchunks;
@@ -370,7 +367,24 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     if (occ < 1) return fail(KLU_TOO_LARGE, "shared-memory regime: zero occupancy");
     const long long ctas = (op.L + W - 1) / W;
     const int grid = static_cast<int>(std::min<long long>(ctas, static_cast<long long>(occ) * sms));
+    if (const char* d = std::getenv("KLUJAX_CUDA_DBG")) a.dbg = std::atoi(d);
+    static const bool do_prof = std::getenv("KLUJAX_CUDA_PROFILE") != nullptr;
+    unsigned long long* dprof = nullptr;
+    if (do_prof) {
+        cudaMalloc(reinterpret_cast<void**>(&dprof), 64);
+        cudaMemset(dprof, 0, 64);
+        a.prof = dprof;
+    }
     kern<<<grid, threads, smem, op.st>>>(a);
+    if (do_prof) {
+        unsigned long long h[8];
+        cudaStreamSynchronize(op.st);
+        cudaMemcpy(h, dprof, 64, cudaMemcpyDeviceToHost);
+        cudaFree(dprof);
+        const double nw = h[5] ? static_cast<double>(h[5]) : 1.0, per = static_cast<double>(op.L) / nw;
+        std::fprintf(stderr, "[PHASES] L=%d W=%d grid=%d warps=%llu cycles/system: load+scale %.0f | rhs %.0f | ring-wait %.0f | run %.0f | store %.0f\n",
+                     op.L, W, grid, h[5], h[0] / nw / per, h[1] / nw / per, h[2] / nw / per, h[3] / nw / per, h[4] / nw / per);
+    }
     CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -314,80 +314,99 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
 
 bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out) {
     out = PackedProgram();
+    constexpr int LW = 32, LINES = kChunkWords / LW;
     const int nx = (prog.mode == PM_FACTOR) ? 0 : lay.n * prog.rc;
-    out.zero_slot = lay.n_val + nx;
-    out.n_slots = out.zero_slot + 1;
-    if (out.n_slots > 16383) return false;  // 14-bit slot fields, 0x3FFF = no pivot operand
-    const uint32_t zero_word = (static_cast<uint32_t>(out.zero_slot) << 16) | out.zero_slot;
-    out.zero_word = zero_word;
-    constexpr int CH = kChunkLines, MAXRUN = kChunkLines - 2;
-    int line = CH, nbatch_in_chunk = 0;  // forces a first chunk
+    out.zero_slot = lay.n_val + nx;  // then ONE (= 1), then TRASH (write-only)
+    out.n_slots = out.zero_slot + 3;
+    if (out.n_slots > 16383) return false;
+    const uint32_t ZERO = out.zero_slot, ONE = ZERO + 1, TRASH = ZERO + 2;
+    auto opword = [](uint32_t a, uint32_t b) { return (a << 18) | (b << 4); };
+    auto hdword = [](uint32_t o, uint32_t d, bool track, bool pivot) {
+        return (o << 18) | (d << 4) | (track ? 1u : 0u) | (pivot ? 2u : 0u);
+    };
+    const uint32_t idle_op = opword(ZERO, ZERO), idle_hd = hdword(TRASH, ONE, false, false);
+    // a batch = control line + header line + 2*trips operand lines; the last line of a
+    // chunk is kept for the terminator (control word 0)
+    const int MAXTRIPS = (LINES - 3) / 2;
+    int line = LINES;  // forces a first chunk
     size_t chunk_base = 0;
+    auto close_chunk = [&]() {
+        if (out.nchunks)
+            for (int lane = 0; lane < LW; ++lane) out.stream[chunk_base + static_cast<size_t>(line) * LW + lane] = 0;
+    };
     auto open_chunk = [&]() {
+        close_chunk();
         chunk_base = out.stream.size();
-        out.stream.resize(chunk_base + static_cast<size_t>(CH) * 32, zero_word);
-        for (int lane = 0; lane < 32; ++lane) out.stream[chunk_base + lane] = 0;  // empty directory
-        line = 1;
-        nbatch_in_chunk = 0;
+        out.stream.resize(chunk_base + kChunkWords, idle_op);
+        line = 0;
         out.nchunks++;
     };
     std::vector<long> f;
-    std::vector<int> choice;
+    std::vector<int> choice, grp;
     for (int l = 0; l < prog.nlevels; ++l) {
-        const int tb = prog.level_ptr[l], te = prog.level_ptr[l + 1], T = te - tb;
-        // Tasks of a level are sorted by dot length (longest first).  Dynamic program over
-        // that order: a batch takes the next 32/g tasks and gives each g lanes (run =
-        // ceil(longest/g) operand lines + one header line + a log2(g)-step shuffle reduce).
-        f.assign(T + 1, 0);
-        choice.assign(T, 0);
-        for (int i = T - 1; i >= 0; --i) {
-            long best = -1;
-            int best_lg = -1;
-            for (int lg = 0; lg <= 5; ++lg) {
-                const int g = 1 << lg, cnt = std::min(32 >> lg, T - i);
-                const int run = (prog.tasks[tb + i].plen + g - 1) / g;
-                if (run > MAXRUN) continue;
-                const long c = run + 2 + lg + f[i + cnt];
-                if (best < 0 || c < best) {
-                    best = c;
-                    best_lg = lg;
+        const int tb = prog.level_ptr[l], te = prog.level_ptr[l + 1];
+        // pivots (reciprocal + singularity test) get batches of their own so that every
+        // batch finishes all of its tasks the same way
+        for (int pass = 0; pass < 2; ++pass) {
+            grp.clear();
+            for (int t = tb; t < te; ++t)
+                if ((prog.tasks[t].kind == TK_RECIP) == (pass == 1)) grp.push_back(t);
+            const int T = static_cast<int>(grp.size());
+            if (!T) continue;
+            // Tasks are sorted by dot length (longest first).  Dynamic program over that
+            // order: a batch takes the next 32/g tasks and gives each g lanes; its cost is
+            // a fixed part, one unit per pair of operand lines and one per reduction step.
+            f.assign(T + 1, 0);
+            choice.assign(T, 0);
+            for (int i = T - 1; i >= 0; --i) {
+                long best = -1;
+                int best_lg = -1;
+                for (int lg = 0; lg <= 5; ++lg) {
+                    const int g = 1 << lg, cnt = std::min(LW >> lg, T - i);
+                    const int run = (prog.tasks[grp[i]].plen + g - 1) / g;
+                    const int trips = std::max(1, (run + 1) / 2);
+                    if (trips > MAXTRIPS) continue;
+                    const long c = 4 + 2 * trips + lg + f[i + cnt];
+                    if (best < 0 || c < best) {
+                        best = c;
+                        best_lg = lg;
+                    }
                 }
+                if (best_lg < 0) return false;  // a dot product too long for one chunk
+                f[i] = best;
+                choice[i] = best_lg;
             }
-            if (best_lg < 0) return false;  // a dot product too long for one chunk
-            f[i] = best;
-            choice[i] = best_lg;
-        }
-        for (int i = 0; i < T;) {
-            const int lg = choice[i], g = 1 << lg, cnt = std::min(32 >> lg, T - i);
-            const int t0 = tb + i, t1 = t0 + cnt;
-            const int run = (prog.tasks[t0].plen + g - 1) / g;
-            if (line + 1 + run > CH || nbatch_in_chunk == 32) open_chunk();
-            const bool last = (t1 == te);
-            out.stream[chunk_base + nbatch_in_chunk] = 0x80000000u | static_cast<uint32_t>(run) |
-                                                       (static_cast<uint32_t>(lg) << 8) |
-                                                       (last ? (1u << 11) : 0u);
-            const size_t base = chunk_base + static_cast<size_t>(line) * 32;
-            for (int lane = 0; lane < 32; ++lane) out.stream[base + lane] = 0;  // TK_NOP headers
-            for (int t = t0; t < t1; ++t) {
-                const Task& tk = prog.tasks[t];
-                const int lead = (t - t0) * g;
-                const uint32_t div = tk.div >= 0 ? static_cast<uint32_t>(tk.div) : 0x3FFFu;
-                out.stream[base + lead] = (static_cast<uint32_t>(tk.kind) << 28) |
-                                          (static_cast<uint32_t>(tk.out) << 14) | div;
-                for (int q = 0; q < tk.plen; ++q) {
-                    const int lane = lead + (q % g), row = q / g;
-                    out.stream[base + 32 * static_cast<size_t>(1 + row) + lane] =
-                        (static_cast<uint32_t>(prog.pa[tk.pbeg + q]) << 16) |
-                        static_cast<uint32_t>(prog.pb[tk.pbeg + q]);
+            for (int i = 0; i < T;) {
+                const int lg = choice[i], g = 1 << lg, cnt = std::min(LW >> lg, T - i);
+                const int run = (prog.tasks[grp[i]].plen + g - 1) / g;
+                const int trips = std::max(1, (run + 1) / 2);
+                if (line + 2 + 2 * trips + 1 > LINES) open_chunk();
+                const uint32_t cw = 0x80000000u | static_cast<uint32_t>(trips) |
+                                    (static_cast<uint32_t>(lg + (pass == 1 ? 6 : 0)) << 8);
+                const size_t base = chunk_base + static_cast<size_t>(line) * LW;
+                for (int lane = 0; lane < LW; ++lane) {
+                    out.stream[base + lane] = cw;
+                    out.stream[base + LW + lane] = idle_hd;
                 }
+                for (int k = 0; k < cnt; ++k) {
+                    const Task& tk = prog.tasks[grp[i + k]];
+                    const int lead = k * g;
+                    const uint32_t div = tk.div >= 0 ? static_cast<uint32_t>(tk.div) : ONE;
+                    out.stream[base + LW + lead] = hdword(tk.out, div, tk.kind == TK_MUL_TRACK, pass == 1);
+                    for (int q = 0; q < tk.plen; ++q) {
+                        const int lane = lead + (q % g), row = q / g;
+                        out.stream[base + static_cast<size_t>(LW) * (2 + row) + lane] =
+                            opword(prog.pa[tk.pbeg + q], prog.pb[tk.pbeg + q]);
+                    }
+                }
+                line += 2 + 2 * trips;
+                out.nbatch++;
+                out.lines_used += 2 + 2 * trips;
+                i += cnt;
             }
-            line += 1 + run;
-            nbatch_in_chunk++;
-            out.nbatch++;
-            out.lines_used += 1 + run;
-            i += cnt;
         }
     }
+    close_chunk();
     return true;
 }
 

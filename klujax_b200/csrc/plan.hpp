@@ -75,17 +75,21 @@ void build_layout(const CscPattern& A, const Ordering& ord, const PivotPlan& piv
 void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
                    int rc, TaskProgram& prog, int split = 0);
 
-// Packed instruction stream of the shared-memory (small-matrix) regime.  The stream is cut
-// into chunks of kChunkLines lines of 32 words (one word per lane); a chunk is what one TMA
-// bulk copy brings into the shared-memory ring.  Line 0 of a chunk is its directory: word i
-// describes batch i of the chunk (0 = end): bit31 valid | run (bits 0-7) | log2 g (bits 8-10)
-// | level-ends-here (bit 11).  A batch is one header line (per lane: kind<<28 | out<<14 |
-// pivot slot) followed by `run` operand lines (per lane: a<<16 | b, zero_word = idle lane).
-constexpr int kChunkLines = 32;
+// Packed instruction stream of the shared-memory (small-matrix) regime: one warp per system,
+// one 32-bit word per lane and line.  The stream is cut into chunks of kChunkWords words,
+// the unit one TMA bulk copy brings into the shared-memory ring.  A chunk is a sequence of
+// batches closed by a terminator line (control word 0).  A batch is
+//   control line : the same word in every lane: bit31 | trips (bits 0-7) | type (bits 8-11),
+//                  type = log2 g (+6 for a batch of pivots), g = lanes sharing one dot product
+//   header line  : per lane  out<<18 | (pivot slot or ONE)<<4 | is-pivot<<1 | is-L-entry
+//   2*trips operand lines: per lane  a<<18 | b<<4
+// Idle lanes multiply the ZERO slot and write to the TRASH slot, so a batch runs without any
+// lane-dependent branch; every batch ends with a warp barrier.
+constexpr int kChunkWords = 1024;
 struct PackedProgram {
-    std::vector<uint32_t> stream;  // nchunks * kChunkLines * 32 words
-    int nchunks = 0, nbatch = 0, zero_slot = 0, n_slots = 0;  // n_slots includes X and the zero slot
-    uint32_t zero_word = 0;
+    std::vector<uint32_t> stream;  // nchunks * kChunkWords
+    int nchunks = 0, nbatch = 0;
+    int zero_slot = 0, n_slots = 0;  // slots: values | X | ZERO | ONE | TRASH
     int64_t lines_used = 0;
 };
 bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out);
