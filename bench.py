@@ -319,7 +319,6 @@ def main():
             _cabi.check(f_so(symh, L, _cabi.u64p(nh), L, n, r, P(b_d), P(x_d), sp))
         launches_per_step = 3
 
-    info = _cabi.symbolic_info(int(sym.handle), cx) if w.name in ("cfg5", "cfg2") else None
     flush = None
     if w.name == "cfg2":  # working set fits in the 126 MB L2: evict it between timed steps
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -331,6 +330,7 @@ def main():
 
     step()  # seeds the pivot sequence (one-time host stage), not a timed step
     torch.cuda.synchronize()
+    info = _cabi.symbolic_info(int(sym.handle), cx)
     for _ in range(args.warmup):
         step()
     barrier()

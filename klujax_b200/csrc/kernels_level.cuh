@@ -27,38 +27,41 @@ namespace kb {
 
 struct LevelProg {
     int ntasks = 0, nlevels = 0;
-    int *d_out = nullptr, *d_div = nullptr, *d_pbeg = nullptr, *d_plen = nullptr, *d_kind = nullptr;
-    int *d_pa = nullptr, *d_pb = nullptr, *d_level_ptr = nullptr;
+    int4* d_task = nullptr;   // per task: out, pivot slot (-1 none), first pair, plen | kind << 24
+    int2* d_pair = nullptr;   // operand slots
+    int* d_level_ptr = nullptr;
     int max_level_tasks = 0;
     int64_t n_mac = 0;
     ~LevelProg() {
-        for (int* p : {d_out, d_div, d_pbeg, d_plen, d_kind, d_pa, d_pb, d_level_ptr})
-            if (p) cudaFree(p);
+        if (d_task) cudaFree(d_task);
+        if (d_pair) cudaFree(d_pair);
+        if (d_level_ptr) cudaFree(d_level_ptr);
     }
     bool upload(const SlotLayout& lay, const TaskProgram& tp, std::string& err) {
         (void)lay;
         ntasks = static_cast<int>(tp.tasks.size());
         nlevels = tp.nlevels;
         n_mac = tp.n_mac;
-        std::vector<int> out(ntasks), dv(ntasks), pbeg(ntasks), plen(ntasks), kind(ntasks);
+        std::vector<int4> rec(std::max(ntasks, 1));
         for (int t = 0; t < ntasks; ++t) {
-            out[t] = tp.tasks[t].out;
-            dv[t] = tp.tasks[t].div;
-            pbeg[t] = tp.tasks[t].pbeg;
-            plen[t] = tp.tasks[t].plen;
-            kind[t] = tp.tasks[t].kind;
+            const Task& k = tp.tasks[t];
+            if (k.plen >= (1 << 24)) {
+                err = "dot product too long for the level program";
+                return false;
+            }
+            rec[t] = make_int4(k.out, k.div, k.pbeg, k.plen | (static_cast<int>(k.kind) << 24));
         }
+        std::vector<int2> pr(std::max<size_t>(tp.pa.size(), 1));
+        for (size_t q = 0; q < tp.pa.size(); ++q) pr[q] = make_int2(tp.pa[q], tp.pb[q]);
         for (int l = 0; l < nlevels; ++l)
             max_level_tasks = std::max(max_level_tasks, tp.level_ptr[l + 1] - tp.level_ptr[l]);
-        auto up = [&](int** d, const std::vector<int>& v) {
-            const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(int);
-            if (cudaMalloc(reinterpret_cast<void**>(d), bytes) != cudaSuccess) return false;
-            return v.empty() ||
-                   cudaMemcpy(*d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+        auto up = [&](void** d, const void* src, size_t bytes) {
+            if (cudaMalloc(d, std::max<size_t>(bytes, 16)) != cudaSuccess) return false;
+            return bytes == 0 || cudaMemcpy(*d, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
         };
-        if (!up(&d_out, out) || !up(&d_div, dv) || !up(&d_pbeg, pbeg) || !up(&d_plen, plen) ||
-            !up(&d_kind, kind) || !up(&d_pa, tp.pa) || !up(&d_pb, tp.pb) ||
-            !up(&d_level_ptr, tp.level_ptr)) {
+        if (!up(reinterpret_cast<void**>(&d_task), rec.data(), rec.size() * sizeof(int4)) ||
+            !up(reinterpret_cast<void**>(&d_pair), pr.data(), pr.size() * sizeof(int2)) ||
+            !up(reinterpret_cast<void**>(&d_level_ptr), tp.level_ptr.data(), tp.level_ptr.size() * sizeof(int))) {
             err = "level program upload failed (out of device memory?)";
             return false;
         }
@@ -156,7 +159,9 @@ __global__ void lv_rowscale(int L, int n, const int* __restrict__ rs_ptr,
 }
 
 struct LvArgs {
-    const int *out, *div, *pbeg, *plen, *kind, *pa, *pb, *level_ptr;
+    const int4* task;
+    const int2* pair;
+    const int* level_ptr;
     int nlevels, n_val, L, r;
     long long lpad, Q;   // Q = L * r right-hand-side columns in the solve
     void* V;
@@ -169,7 +174,7 @@ struct LvArgs {
 
 // Persistent refactorization: thread per (task, system) inside a level.
 template <typename T>
-__global__ void __launch_bounds__(256) lv_factor(const LvArgs a) {
+__global__ void __launch_bounds__(1024) lv_factor(const LvArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
     V_t* V = static_cast<V_t*>(a.V);
@@ -183,22 +188,25 @@ __global__ void __launch_bounds__(256) lv_factor(const LvArgs a) {
             const int t = tb + static_cast<int>(it / lanes), m = static_cast<int>(it % lanes);
             if (m >= a.L) continue;
             const int sm = a.sysidx ? a.sysidx[m] : m;
-            const int pbeg = __ldg(a.pbeg + t), plen = __ldg(a.plen + t);
+            const int4 rec = __ldg(a.task + t);
+            const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
+            const int2* pr = a.pair + rec.z;
+            V_t* o = V + (long long)rec.x * a.lpad + sm;
+            const V_t o0 = __ldcg(o);
             V_t acc = S::zero();
 #pragma unroll 4
             for (int p = 0; p < plen; ++p) {
-                const V_t x = __ldcg(V + (long long)__ldg(a.pa + pbeg + p) * a.lpad + sm);
-                const V_t y = __ldcg(V + (long long)__ldg(a.pb + pbeg + p) * a.lpad + sm);
+                const int2 ab = __ldg(pr + p);
+                const V_t x = __ldcg(V + (long long)ab.x * a.lpad + sm);
+                const V_t y = __ldcg(V + (long long)ab.y * a.lpad + sm);
                 S::fma_acc(acc, x, y);
             }
-            const int kind = __ldg(a.kind + t);
-            V_t* o = V + (long long)__ldg(a.out + t) * a.lpad + sm;
-            V_t v = S::sub(__ldcg(o), acc);
+            V_t v = S::sub(o0, acc);
             if (kind == TK_RECIP) {
                 if (S::bad_pivot(v)) a.bad[m] = 1;
                 v = S::recip(v);
             } else if (kind >= TK_MUL) {
-                v = S::mul(v, __ldcg(V + (long long)__ldg(a.div + t) * a.lpad + sm));
+                v = S::mul(v, __ldcg(V + (long long)rec.y * a.lpad + sm));
                 if (kind == TK_MUL_TRACK)
                     atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v)));
             }
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(256) lv_factor(const LvArgs a) {
 
 // Persistent triangular solves: thread per (task, right-hand-side column).
 template <typename T>
-__global__ void __launch_bounds__(256) lv_solve(const LvArgs a) {
+__global__ void __launch_bounds__(1024) lv_solve(const LvArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
     const V_t* V = static_cast<const V_t*>(a.V);
@@ -227,17 +235,21 @@ __global__ void __launch_bounds__(256) lv_solve(const LvArgs a) {
             if (q >= a.Q) continue;
             const int m = static_cast<int>(q / a.r);
             const int sm = a.sysidx ? a.sysidx[m] : m;
-            const int pbeg = __ldg(a.pbeg + t), plen = __ldg(a.plen + t);
+            const int4 rec = __ldg(a.task + t);
+            const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
+            const int2* pr = a.pair + rec.z;
+            V_t* o = X + (long long)(rec.x - a.n_val) * a.Q + q;
+            const V_t o0 = __ldcg(o);
             V_t acc = S::zero();
 #pragma unroll 4
             for (int p = 0; p < plen; ++p) {
-                const V_t lu = __ldg(V + (long long)__ldg(a.pa + pbeg + p) * a.lpad + sm);
-                const V_t xv = __ldcg(X + (long long)(__ldg(a.pb + pbeg + p) - a.n_val) * a.Q + q);
+                const int2 ab = __ldg(pr + p);
+                const V_t lu = __ldg(V + (long long)ab.x * a.lpad + sm);
+                const V_t xv = __ldcg(X + (long long)(ab.y - a.n_val) * a.Q + q);
                 S::fma_acc(acc, lu, xv);
             }
-            V_t* o = X + (long long)(__ldg(a.out + t) - a.n_val) * a.Q + q;
-            V_t v = S::sub(__ldcg(o), acc);
-            if (__ldg(a.kind + t) >= TK_MUL) v = S::mul(v, __ldg(V + (long long)__ldg(a.div + t) * a.lpad + sm));
+            V_t v = S::sub(o0, acc);
+            if (kind >= TK_MUL) v = S::mul(v, __ldg(V + (long long)rec.y * a.lpad + sm));
             *o = v;
         }
         if (l + 1 < a.nlevels) grid_barrier(a.barrier, gridDim.x, target);
@@ -349,19 +361,18 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
         lv_rowscale<T><<<static_cast<unsigned>((rt + 255) / 256), 256, 0, c.st>>>(
             c.L, c.n, c.rs_ptr, c.rs_slot, c.sysidx, V, Rs, lpad);
         LvArgs a;
-        a.out = pf->d_out; a.div = pf->d_div; a.pbeg = pf->d_pbeg; a.plen = pf->d_plen;
-        a.kind = pf->d_kind; a.pa = pf->d_pa; a.pb = pf->d_pb; a.level_ptr = pf->d_level_ptr;
+        a.task = pf->d_task; a.pair = pf->d_pair; a.level_ptr = pf->d_level_ptr;
         a.nlevels = pf->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = 1; a.lpad = lpad; a.Q = c.L;
         a.V = V; a.X = nullptr; a.sysidx = c.sysidx; a.barrier = barrier; a.bad = bad; a.growth2 = growth2;
-        if (!chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, lv_factor<T>, 256, 0), "occupancy")) {
+        if (!chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, lv_factor<T>, 1024, 0), "occupancy")) {
             cleanup();
             return KLU_OUT_OF_MEMORY;
         }
-        const long long max_items = (long long)pf->max_level_tasks * ((c.L + 31) & ~31);
+        const long long avg_items = (long long)pf->ntasks * ((c.L + 31) & ~31) / std::max(1, pf->nlevels);
         int grid = static_cast<int>(std::min<long long>((long long)blocks_per_sm * c.num_sms,
-                                                        std::max<long long>(1, (max_items + 255) / 256)));
+                                                        std::max<long long>(1, (2 * avg_items + 1023) / 1024)));
         void* args[] = {&a};
-        if (!chk(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lv_factor<T>), dim3(grid), dim3(256),
+        if (!chk(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lv_factor<T>), dim3(grid), dim3(1024),
                                              args, 0, c.st), "launch lv_factor")) {
             cleanup();
             return KLU_OUT_OF_MEMORY;
@@ -382,19 +393,18 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
             c.L, c.n, c.r, static_cast<const V_t*>(c.b), c.b_stride, tr ? c.q : c.pnum, tr ? 0 : 1,
             Rs, lpad, c.sysidx, X);
         LvArgs a;
-        a.out = ps->d_out; a.div = ps->d_div; a.pbeg = ps->d_pbeg; a.plen = ps->d_plen;
-        a.kind = ps->d_kind; a.pa = ps->d_pa; a.pb = ps->d_pb; a.level_ptr = ps->d_level_ptr;
+        a.task = ps->d_task; a.pair = ps->d_pair; a.level_ptr = ps->d_level_ptr;
         a.nlevels = ps->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = c.r; a.lpad = lpad; a.Q = Q;
         a.V = V; a.X = X; a.sysidx = c.sysidx; a.barrier = barrier + 8; a.bad = bad; a.growth2 = growth2;
-        if (!chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, lv_solve<T>, 256, 0), "occupancy")) {
+        if (!chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, lv_solve<T>, 1024, 0), "occupancy")) {
             cleanup();
             return KLU_OUT_OF_MEMORY;
         }
-        const long long max_items = (long long)ps->max_level_tasks * ((Q + 31) & ~31LL);
+        const long long avg_items = (long long)ps->ntasks * ((Q + 31) & ~31LL) / std::max(1, ps->nlevels);
         int grid = static_cast<int>(std::min<long long>((long long)blocks_per_sm * c.num_sms,
-                                                        std::max<long long>(1, (max_items + 255) / 256)));
+                                                        std::max<long long>(1, (2 * avg_items + 1023) / 1024)));
         void* args[] = {&a};
-        if (!chk(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lv_solve<T>), dim3(grid), dim3(256),
+        if (!chk(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lv_solve<T>), dim3(grid), dim3(1024),
                                              args, 0, c.st), "launch lv_solve")) {
             cleanup();
             return KLU_OUT_OF_MEMORY;

@@ -258,7 +258,14 @@ static int get_level_prog(Symbolic* S, int cx, int mode, LevelProg** out) {
     auto it = sd.level.find(key);
     if (it == sd.level.end()) {
         TaskProgram tp;
-        build_program(S->ord, sd.piv, sd.lay, mode, 1, tp);
+        // level regime: one thread per (task, system); short partial updates keep the time per
+        // level at one L2 round trip.  Huge factorizations (cfg 3: 2.6e8 multiply-adds) keep
+        // the dot form: one task per multiply-add group would not fit.
+        // (measured: cfg 4 refactor 193 -> 69 ms with per-level partial updates; the multi-RHS
+        // solve of cfg 3 prefers groups of >= 8 multiply-adds: fewer read-modify-writes of X)
+        int split = (mode == PM_FACTOR) ? (sd.lay.n_lu >= 4000000 ? 0 : 2) : 3;
+        if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_SPLIT")) split = std::atoi(e);
+        build_program(S->ord, sd.piv, sd.lay, mode, 1, tp, split);
         auto lp = std::make_unique<LevelProg>();
         std::string err;
         if (!lp->upload(sd.lay, tp, err)) return fail(KLU_OUT_OF_MEMORY, err);

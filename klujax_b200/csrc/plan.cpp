@@ -115,6 +115,7 @@ struct Leveler {
     std::vector<int> val_level, read_level;
     TaskProgram& prog;
     bool split;
+    int min_group = 1;
     std::vector<std::pair<int, int>> order;  // (ready level, pair index)
     Leveler(int nidx, TaskProgram& p, bool split_) : val_level(nidx, 0), read_level(nidx, 0), prog(p), split(split_) {}
 
@@ -160,10 +161,13 @@ struct Leveler {
         }
         int ob = 0;
         while (ob < np) {
+            // a partial update takes every pair that is ready at one level, and keeps taking
+            // later ones until it holds at least min_group pairs
             int oe = ob;
-            while (oe < np && order[oe].first == order[ob].first) ++oe;
+            while (oe < np && (order[oe].first == order[ob].first || oe - ob < min_group)) ++oe;
+            while (oe < np && order[oe].first == order[oe - 1].first) ++oe;
             if (oe == np) break;  // the last group carries the finishing operation
-            emit(TK_SUB, out, -1, order[ob].first, pairs, ob, oe);
+            emit(TK_SUB, out, -1, order[oe - 1].first, pairs, ob, oe);
             ob = oe;
         }
         // last group (possibly empty) + finish; it may have to wait for the pivot
@@ -187,8 +191,9 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
     const bool do_tsolve = (mode == PM_FACTOR_TSOLVE || mode == PM_TSOLVE);
     const int nx = (do_solve || do_tsolve) ? n * rc : 0;
     // split: 0 = dot form everywhere, 1 = as-soon-as-possible updates in the triangular
-    // solves only, 2 = everywhere
+    // solves only, 2 = everywhere, 3 = everywhere in groups of at least 8 multiply-adds
     Leveler lv(lay.n_val + nx, prog, split >= 2);
+    if (split == 3) lv.min_group = 8;
     const std::vector<int> k1of = block_of_column(ord);
     auto xs = [&](int k, int c) { return lay.n_val + k * rc + c; };
     std::vector<std::pair<int, int>> pairs;
