@@ -115,6 +115,8 @@ struct SmallArgs {
     // [1] further right-hand-side chunks (solve only)
     const uint32_t* stream[2];
     int nchunks[2];
+    uint32_t ctrl[2][kMaxBatches];          // warp-uniform control words (constant bank)
+    uint16_t chunk_ptr[2][kMaxChunks + 1];  // first batch of each chunk
     int W;                   // systems (= consumer warps) per CTA
     int n, n_val, n_slots, zero_slot, rc, nz, flags;
     const int* coo_dst;      // [nz] slot of each COO entry of this call, -1 = not in pattern
@@ -136,7 +138,6 @@ struct SmallArgs {
     double* growth;
     int L;
     unsigned long long* prof;  // optional [8] cycle counters (KLUJAX_CUDA_PROFILE=1)
-    int dbg;                   // KLUJAX_CUDA_DBG bisection flags (wrong results!), 0 in production
 };
 
 constexpr int kRingBufs = 3;                                   // chunks in flight per CTA
@@ -191,80 +192,50 @@ __device__ __forceinline__ typename Sc<T>::V* slot_lo(unsigned char* Vb, uint32_
     return reinterpret_cast<typename Sc<T>::V*>(Vb + ((w >> SH) & (0x3FFF0u >> SH)));
 }
 
-// Runs every batch of one chunk out of the shared-memory ring.  Per batch and lane:
+// Runs the batches [b0, b1) of one chunk out of the shared-memory ring.  Per batch and lane:
 // acc = sum a*b over 2*trips operand lines; tree-reduce over g lanes; then
-// V[out] = (V[out] - acc) * V[pivot-or-ONE], or the reciprocal for a batch of pivots.
-// The next batch's control and header words are fetched before the current batch stores.
+// V[out] = (V[out] - acc) [* V[pivot reciprocal]], or the reciprocal for a lane that finishes
+// a pivot.  Everything that steers control flow comes from the control words in the
+// parameter space, i.e. from uniform registers.
 template <typename T>
-__device__ __forceinline__ void run_chunk(unsigned char* __restrict__ Vb,
-                                          const uint32_t* __restrict__ p, bool& bad, double& gmax,
-                                          const int dbg) {
+__device__ __forceinline__ void run_chunk(const SmallArgs& a, int pi, int b0, int b1,
+                                          unsigned char* __restrict__ Vb,
+                                          const uint32_t* __restrict__ p, bool& bad, double& gmax) {
     using S = Sc<T>;
     using V_t = typename S::V;
-    uint32_t cw = p[0], h = p[32];
-    while (cw) {
+    for (int b = b0; b < b1; ++b) {
+        const uint32_t cw = a.ctrl[pi][b];
         int trips = cw & 0xFF;
-        const int type = (cw >> 8) & 0xF;
-        const uint32_t* ops = p + 64;
+        const int lg = (cw >> 8) & 7;
+        const uint32_t h = p[0];
+        const uint32_t* ops = p + 32;
         p = ops + trips * 64;
-        const uint32_t ncw = p[0], nh = p[32];
         V_t* po = slot_hi<T>(Vb, h);
         const V_t vo = *po;
-        const V_t vd = *slot_lo<T>(Vb, h);
         typename S::Acc c = S::acc0();
         do {
             const uint32_t w0 = ops[0], w1 = ops[32];
             ops += 64;
-            V_t a0, b0, a1, b1;
-            if (dbg & 1) {  // no operand loads
-                a0 = b0 = a1 = b1 = vo;
-            } else {
-                a0 = *slot_hi<T>(Vb, w0), b0 = *slot_lo<T>(Vb, w0);
-                a1 = *slot_hi<T>(Vb, w1), b1 = *slot_lo<T>(Vb, w1);
-            }
-            if (!(dbg & 2)) {
-                S::mac(c, a0, b0, 0);
-                S::mac(c, a1, b1, 1);
-            } else if (w0 == 0x12345678u) {
-                S::mac(c, a0, b0, 0);
-                S::mac(c, a1, b1, 1);
-            }
+            const V_t a0 = *slot_hi<T>(Vb, w0), b0v = *slot_lo<T>(Vb, w0);
+            const V_t a1 = *slot_hi<T>(Vb, w1), b1v = *slot_lo<T>(Vb, w1);
+            S::mac(c, a0, b0v, 0);
+            S::mac(c, a1, b1v, 1);
         } while (--trips);
         V_t acc = S::fold(c);
-#define KB_RED(o) acc = S::add(acc, S::shfl_down(acc, o, 32))
-#define KB_FINISH                                              \
-    {                                                          \
-        const V_t t = S::mul(S::sub(vo, acc), vd);             \
-        gmax = fmax(gmax, (h & 1u) ? S::mag2(t) : 0.0);        \
-        *po = t;                                               \
-    }
-#define KB_PIVOT                                               \
-    {                                                          \
-        const V_t t = S::sub(vo, acc);                         \
-        if (h & 2u) bad |= S::bad_pivot(t);                    \
-        *po = S::recip(t);                                     \
-    }
-        // a group leader only ever reads lanes of its own group
-        switch ((dbg & 8) ? 0 : type) {
-            case 0: KB_FINISH break;
-            case 1: KB_RED(1); KB_FINISH break;
-            case 2: KB_RED(2); KB_RED(1); KB_FINISH break;
-            case 3: KB_RED(4); KB_RED(2); KB_RED(1); KB_FINISH break;
-            case 4: KB_RED(8); KB_RED(4); KB_RED(2); KB_RED(1); KB_FINISH break;
-            case 5: KB_RED(16); KB_RED(8); KB_RED(4); KB_RED(2); KB_RED(1); KB_FINISH break;
-            case 6: KB_PIVOT break;
-            case 7: KB_RED(1); KB_PIVOT break;
-            case 8: KB_RED(2); KB_RED(1); KB_PIVOT break;
-            case 9: KB_RED(4); KB_RED(2); KB_RED(1); KB_PIVOT break;
-            case 10: KB_RED(8); KB_RED(4); KB_RED(2); KB_RED(1); KB_PIVOT break;
-            default: KB_RED(16); KB_RED(8); KB_RED(4); KB_RED(2); KB_RED(1); KB_PIVOT break;
+        // lane-group tree reduction; a group leader only ever reads lanes of its own group
+        for (int s = lg; s-- > 0;) acc = S::add(acc, S::shfl_down(acc, 1 << s, 32));
+        const V_t d = S::sub(vo, acc);
+        V_t t = d;
+        if (cw & kCwMul) t = S::mul(d, *slot_lo<T>(Vb, h));
+        if (cw & kCwTrack) gmax = fmax(gmax, (h & 1u) ? S::mag2(t) : 0.0);
+        if (cw & kCwPivot) {
+            if (h & 2u) {
+                bad |= S::bad_pivot(d);
+                t = S::recip(d);
+            }
         }
-#undef KB_RED
-#undef KB_FINISH
-#undef KB_PIVOT
-        if (!(dbg & 4)) __syncwarp();
-        cw = ncw;
-        h = nh;
+        *po = t;
+        __syncwarp();
     }
 }
 
@@ -273,7 +244,7 @@ __device__ __forceinline__ void run_chunk(unsigned char* __restrict__ Vb,
 // bulk copies; full/empty mbarriers pace it.  All consumer warps of a CTA walk the same
 // program, so the schedule is read from L2 once per CTA, not once per system.
 template <typename T>
-__global__ void __launch_bounds__(544, 1) small_kernel(const SmallArgs a) {
+__global__ void __launch_bounds__(544, 1) small_kernel(const __grid_constant__ SmallArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -420,7 +391,8 @@ __global__ void __launch_bounds__(544, 1) small_kernel(const SmallArgs a) {
                 if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
                 const uint32_t* base = ring + buf * kChunkWords;
                 // every consumer warp runs the program (idle ones on scratch values)
-                run_chunk<T>(reinterpret_cast<unsigned char*>(V), base + lane, bad, gmax, a.dbg);
+                run_chunk<T>(a, pi, a.chunk_ptr[pi][c], a.chunk_ptr[pi][c + 1],
+                             reinterpret_cast<unsigned char*>(V), base + lane, bad, gmax);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + buf);
                 if (prof) { const long long t1 = clock64(); t_run += t1 - t0; t0 = t1; }

@@ -2,6 +2,8 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 
 namespace kb {
@@ -330,32 +332,28 @@ bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram&
         return (o << 18) | (d << 4) | (track ? 1u : 0u) | (pivot ? 2u : 0u);
     };
     const uint32_t idle_op = opword(ZERO, ZERO), idle_hd = hdword(TRASH, ONE, false, false);
-    // a batch = control line + header line + 2*trips operand lines; the last line of a
-    // chunk is kept for the terminator (control word 0)
-    const int MAXTRIPS = (LINES - 3) / 2;
+    // a batch = header line + 2*trips operand lines
+    const int MAXTRIPS = (LINES - 1) / 2;
     int line = LINES;  // forces a first chunk
     size_t chunk_base = 0;
-    auto close_chunk = [&]() {
-        if (out.nchunks)
-            for (int lane = 0; lane < LW; ++lane) out.stream[chunk_base + static_cast<size_t>(line) * LW + lane] = 0;
-    };
     auto open_chunk = [&]() {
-        close_chunk();
         chunk_base = out.stream.size();
         out.stream.resize(chunk_base + kChunkWords, idle_op);
+        out.chunk_ptr.push_back(static_cast<uint16_t>(out.nbatch));
         line = 0;
         out.nchunks++;
     };
     std::vector<long> f;
     std::vector<int> choice, grp;
+    // measured on B200 (in-kernel cycle counters): a batch costs ~700 cycles before its first
+    // operand line, ~75 per pair of operand lines, ~40 per reduction step
+    long cost_fixed = 18, cost_trip = 2, cost_lg = 1;
+    if (const char* e = std::getenv("KLUJAX_CUDA_PACK_COST")) std::sscanf(e, "%ld,%ld,%ld", &cost_fixed, &cost_trip, &cost_lg);
     for (int l = 0; l < prog.nlevels; ++l) {
         const int tb = prog.level_ptr[l], te = prog.level_ptr[l + 1];
-        // pivots (reciprocal + singularity test) get batches of their own so that every
-        // batch finishes all of its tasks the same way
-        for (int pass = 0; pass < 2; ++pass) {
+        {
             grp.clear();
-            for (int t = tb; t < te; ++t)
-                if ((prog.tasks[t].kind == TK_RECIP) == (pass == 1)) grp.push_back(t);
+            for (int t = tb; t < te; ++t) grp.push_back(t);
             const int T = static_cast<int>(grp.size());
             if (!T) continue;
             // Tasks are sorted by dot length (longest first).  Dynamic program over that
@@ -371,7 +369,7 @@ bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram&
                     const int run = (prog.tasks[grp[i]].plen + g - 1) / g;
                     const int trips = std::max(1, (run + 1) / 2);
                     if (trips > MAXTRIPS) continue;
-                    const long c = 4 + 2 * trips + lg + f[i + cnt];
+                    const long c = cost_fixed + cost_trip * trips + cost_lg * lg + f[i + cnt];
                     if (best < 0 || c < best) {
                         best = c;
                         best_lg = lg;
@@ -385,34 +383,34 @@ bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram&
                 const int lg = choice[i], g = 1 << lg, cnt = std::min(LW >> lg, T - i);
                 const int run = (prog.tasks[grp[i]].plen + g - 1) / g;
                 const int trips = std::max(1, (run + 1) / 2);
-                if (line + 2 + 2 * trips + 1 > LINES) open_chunk();
-                const uint32_t cw = 0x80000000u | static_cast<uint32_t>(trips) |
-                                    (static_cast<uint32_t>(lg + (pass == 1 ? 6 : 0)) << 8);
+                if (line + 1 + 2 * trips > LINES) open_chunk();
+                uint32_t cw = static_cast<uint32_t>(trips) | (static_cast<uint32_t>(lg) << 8);
                 const size_t base = chunk_base + static_cast<size_t>(line) * LW;
-                for (int lane = 0; lane < LW; ++lane) {
-                    out.stream[base + lane] = cw;
-                    out.stream[base + LW + lane] = idle_hd;
-                }
+                for (int lane = 0; lane < LW; ++lane) out.stream[base + lane] = idle_hd;
                 for (int k = 0; k < cnt; ++k) {
                     const Task& tk = prog.tasks[grp[i + k]];
                     const int lead = k * g;
                     const uint32_t div = tk.div >= 0 ? static_cast<uint32_t>(tk.div) : ONE;
-                    out.stream[base + LW + lead] = hdword(tk.out, div, tk.kind == TK_MUL_TRACK, pass == 1);
+                    if (tk.kind == TK_RECIP) cw |= kCwPivot;
+                    if (tk.div >= 0) cw |= kCwMul;
+                    if (tk.kind == TK_MUL_TRACK) cw |= kCwTrack;
+                    out.stream[base + lead] = hdword(tk.out, div, tk.kind == TK_MUL_TRACK, tk.kind == TK_RECIP);
                     for (int q = 0; q < tk.plen; ++q) {
                         const int lane = lead + (q % g), row = q / g;
-                        out.stream[base + static_cast<size_t>(LW) * (2 + row) + lane] =
+                        out.stream[base + static_cast<size_t>(LW) * (1 + row) + lane] =
                             opword(prog.pa[tk.pbeg + q], prog.pb[tk.pbeg + q]);
                     }
                 }
-                line += 2 + 2 * trips;
+                out.ctrl.push_back(cw);
+                line += 1 + 2 * trips;
                 out.nbatch++;
-                out.lines_used += 2 + 2 * trips;
+                out.lines_used += 1 + 2 * trips;
                 i += cnt;
             }
         }
     }
-    close_chunk();
-    return true;
+    out.chunk_ptr.push_back(static_cast<uint16_t>(out.nbatch));
+    return out.nbatch <= kMaxBatches && out.nchunks <= kMaxChunks;
 }
 
 }  // namespace kb

@@ -75,19 +75,26 @@ void build_layout(const CscPattern& A, const Ordering& ord, const PivotPlan& piv
 void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
                    int rc, TaskProgram& prog, int split = 0);
 
-// Packed instruction stream of the shared-memory (small-matrix) regime: one warp per system,
-// one 32-bit word per lane and line.  The stream is cut into chunks of kChunkWords words,
-// the unit one TMA bulk copy brings into the shared-memory ring.  A chunk is a sequence of
-// batches closed by a terminator line (control word 0).  A batch is
-//   control line : the same word in every lane: bit31 | trips (bits 0-7) | type (bits 8-11),
-//                  type = log2 g (+6 for a batch of pivots), g = lanes sharing one dot product
-//   header line  : per lane  out<<18 | (pivot slot or ONE)<<4 | is-pivot<<1 | is-L-entry
-//   2*trips operand lines: per lane  a<<18 | b<<4
-// Idle lanes multiply the ZERO slot and write to the TRASH slot, so a batch runs without any
-// lane-dependent branch; every batch ends with a warp barrier.
+// Packed schedule of the shared-memory (small-matrix) regime: one warp per system.
+//
+//  * control words, one per batch, warp-uniform; they travel as KERNEL PARAMETERS (constant
+//    bank), so every branch of the interpreter is a uniform branch:
+//        trips (bits 0-7) | log2 g (bits 8-10) | some lane finishes a pivot (bit 11)
+//        | some lane multiplies by a pivot reciprocal (bit 12) | some lane is an L entry (bit 13)
+//    g = lanes sharing one dot product; chunk_ptr[c] = first batch of chunk c.
+//  * the lane stream, one 32-bit word per lane and line, cut into chunks of kChunkWords words
+//    (the unit one TMA bulk copy brings into the shared-memory ring).  Per batch:
+//        header line  : out<<18 | (pivot slot or ONE)<<4 | is-pivot<<1 | is-L-entry
+//        2*trips operand lines: a<<18 | b<<4
+//    Idle lanes multiply the ZERO slot and write to the TRASH slot: no lane-dependent branch.
 constexpr int kChunkWords = 1024;
+constexpr int kMaxBatches = 1536;  // per program (control words live in the parameter space)
+constexpr int kMaxChunks = 255;
+constexpr uint32_t kCwPivot = 1u << 11, kCwMul = 1u << 12, kCwTrack = 1u << 13;
 struct PackedProgram {
-    std::vector<uint32_t> stream;  // nchunks * kChunkWords
+    std::vector<uint32_t> ctrl;       // nbatch
+    std::vector<uint16_t> chunk_ptr;  // nchunks + 1
+    std::vector<uint32_t> stream;     // nchunks * kChunkWords
     int nchunks = 0, nbatch = 0;
     int zero_slot = 0, n_slots = 0;  // slots: values | X | ZERO | ONE | TRASH
     int64_t lines_used = 0;
