@@ -321,3 +321,99 @@ def test_dot_vs_dense(K, dtype):
     got = np_(K.dot(Ai, Aj, Ax, x))
     for m in range(3):
         assert relerr(got[m], dense(Ai, Aj, Ax[m], 5) @ x[m]) < 1e-13
+
+
+# ------------------------------------------------------------------ structural edge cases
+def _upper_triangular(n, dtype, L, seed=3):
+    r = np.random.default_rng(seed)
+    iu, ju = np.triu_indices(n)
+    keep = (iu == ju) | (r.random(iu.size) < 0.5)
+    Ai, Aj = iu[keep].astype(np.int32), ju[keep].astype(np.int32)
+    Ax = r.standard_normal((L, Ai.size)).astype(dtype)
+    if np.issubdtype(np.dtype(dtype), np.complexfloating):
+        Ax = Ax + 1j * r.standard_normal((L, Ai.size))
+    Ax[:, Ai == Aj] += 4.0
+    return Ai, Aj, Ax
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("regime", ["0", "1"])
+def test_all_singleton_blocks_offdiagonal_backsubstitution(K, oracle, dtype, regime, monkeypatch):
+    """Upper-triangular A: every BTF block is a singleton, all the work is the block
+    back-substitution through the off-diagonal entries (klu_solve / klu_tsolve)."""
+    monkeypatch.setenv("KLUJAX_CUDA_FORCE_REGIME", regime)
+    n, L = 12, 5
+    Ai, Aj, Ax = _upper_triangular(n, dtype, L)
+    b = np.random.default_rng(0).standard_normal((L, n, 3)).astype(dtype)
+    so = oracle.analyze(Ai, Aj, n)
+    assert oracle.symbolic_info(so)["nblocks"] == n
+    with K.analyze(Ai, Aj, n) as sym:
+        assert relerr(np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym)), oracle.solve_with_symbol(Ai, Aj, Ax, b, so)) < X_TOL
+        assert relerr(np_(K.tsolve_with_symbol(Ai, Aj, Ax, b, sym)),
+                      oracle.solve_with_symbol(Ai, Aj, Ax, b, so, transpose=True)) < X_TOL
+    oracle.free_symbolic(so)
+
+
+def test_one_by_one_and_tiny_blocks(K, oracle):
+    # 1x1
+    x = np_(K.solve(np.array([0]), np.array([0]), np.array([[2.0], [4.0], [-8.0]]), np.ones((3, 1, 2))))
+    assert np.allclose(x[:, 0, 0], [0.5, 0.25, -0.125])
+    # block diagonal of a 2x2 and a 3x3 block (natural order inside blocks of size <= 3)
+    A = np.zeros((5, 5))
+    A[:2, :2] = [[4, 1], [2, 5]]
+    A[2:, 2:] = [[6, 1, 0], [1, 7, 2], [3, 0, 8]]
+    Ai, Aj = np.nonzero(A)
+    b = np.arange(10.0).reshape(5, 2)
+    assert relerr(np_(K.solve(Ai, Aj, A[Ai, Aj], b)), np.linalg.solve(A, b)) < 1e-13
+
+
+def test_many_right_hand_sides_in_the_shared_memory_regime(K, oracle):
+    """n_rhs larger than the chunk the value array can hold: the kernel re-runs the
+    solve-only program per chunk while the factors stay in shared memory."""
+    Ai, Aj, Ax, b = synth.ref_style_case(20, 60, 3, 17, np.complex128)
+    so = oracle.analyze(Ai, Aj, 20)
+    with K.analyze(Ai, Aj, 20) as sym:
+        assert relerr(np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym)), oracle.solve_with_symbol(Ai, Aj, Ax, b, so)) < X_TOL
+        with K.factor(Ai, Aj, Ax, sym) as num:
+            assert relerr(np_(K.tsolve_with_numeric(num, b, sym)),
+                          oracle.solve_with_symbol(Ai, Aj, Ax, b, so, transpose=True)) < X_TOL
+    oracle.free_symbolic(so)
+
+
+def test_float64_sax_pattern(K, oracle):
+    """The shared-memory regime in real arithmetic on the cfg2 pattern."""
+    pat = synth.SaxPattern(64, seed=1)
+    L = 40
+    Ax = np.ascontiguousarray(pat.values(0, L).real) * 2.0
+    Ax[:, pat.Ai == pat.Aj] = 1.0
+    b = np.random.default_rng(2).standard_normal((L, 64, 2))
+    so = oracle.analyze(pat.Ai, pat.Aj, 64)
+    with K.analyze(pat.Ai, pat.Aj, 64) as sym:
+        x = np_(K.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, sym))
+    assert relerr(x, oracle.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, so)) < X_TOL
+    assert residual(pat.Ai, pat.Aj, Ax[3], x[3], b[3], 64) < RES_TOL
+    oracle.free_symbolic(so)
+
+
+def test_duplicate_entries_are_rejected(K):
+    Ai, Aj = np.array([0, 0, 1], np.int32), np.array([0, 0, 1], np.int32)
+    with K.analyze(Ai, Aj, 2) as sym:
+        with pytest.raises(K.KlujaxCudaError) as ei:
+            K.solve_with_symbol(Ai, Aj, np.ones((1, 3)), np.ones((1, 2, 1)), sym)
+        assert ei.value.code == -3
+
+
+def test_free_semantics(K):
+    Ai, Aj, Ax, b = synth.ref_style_case(5, 15, 3, 1, np.float64)
+    sym = K.analyze(Ai, Aj, 5)
+    num = K.factor(Ai, Aj, Ax, sym)
+    h = num.handle.copy()
+    assert K.free_numeric(h[:1]) == 1           # element-wise free (klujax.cpp:1282-1288)
+    with pytest.raises(K.KlujaxCudaError):      # a freed element is stale
+        K.solve_with_numeric(h, b, sym)
+    two = K.KLUHandleManager(h[1:], None, owner=False)
+    assert np_(K.solve_with_numeric(two, b[1:], sym)).shape == (2, 5, 1)
+    num.close()                                  # frees the rest; second close is a no-op
+    num.close()
+    assert K.free_symbolic(sym) == 0             # manager path returns 0 (klujax.py:251-253)
+    assert K.free_symbolic(np.uint64(0)) == 0    # null handle: nothing to free

@@ -184,3 +184,26 @@ def test_linearity_property(oracle):
     x12 = oracle.solve_with_symbol(pat.Ai, pat.Aj, Ax, 2 * b1 + b2, sym)
     oracle.free_symbolic(sym)
     assert relerr(x12, 2 * x1 + x2) < 1e-13
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_triangular_all_singleton_blocks(oracle, dtype):
+    """Upper-triangular A: n singleton BTF blocks, only off-diagonal back-substitution."""
+    r = np.random.default_rng(3)
+    n, L = 12, 3
+    iu, ju = np.triu_indices(n)
+    keep = (iu == ju) | (r.random(iu.size) < 0.5)
+    Ai, Aj = iu[keep].astype(np.int32), ju[keep].astype(np.int32)
+    Ax = r.standard_normal((L, Ai.size)).astype(dtype)
+    Ax[:, Ai == Aj] += 4.0
+    b = r.standard_normal((L, n, 2)).astype(dtype)
+    sym = oracle.analyze(Ai, Aj, n)
+    info = oracle.symbolic_info(sym)
+    assert info["nblocks"] == n and info["nzoff"] == Ai.size - n
+    x = oracle.solve_with_symbol(Ai, Aj, Ax, b, sym)
+    xt = oracle.solve_with_symbol(Ai, Aj, Ax, b, sym, transpose=True)
+    oracle.free_symbolic(sym)
+    for m in range(L):
+        A = dense(Ai, Aj, Ax[m], n)
+        assert relerr(x[m], np.linalg.solve(A, b[m])) < 1e-12
+        assert relerr(xt[m], np.linalg.solve(A.T, b[m])) < 1e-12
