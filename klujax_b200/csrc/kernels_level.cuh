@@ -4,9 +4,10 @@
 // Layout in HBM: values are batch-interleaved, V[slot][system] (and
 // X[row][system*n_rhs + column] for the solves), so consecutive threads handle
 // consecutive systems / right-hand sides and every load of a value is
-// coalesced.  One persistent cooperative kernel walks the level sets of the
-// static task DAG (plan.hpp) with a grid-wide barrier between levels; there is
-// no sparsity logic on the device, only index lists shared by the whole batch.
+// coalesced.  Systems (and right-hand-side columns) never interact, so a CTA owns a
+// slice of the batch axis and walks ALL level sets of the static task DAG
+// (plan.hpp) on it alone, with __syncthreads() between levels - no grid barrier.
+// There is no sparsity logic on the device, only index lists shared by the batch.
 //
 // Replaces klu_refactor / klu_solve / klu_tsolve as called per system at
 // /root/reference/klujax.cpp:781, :911, :1087, :1220 and the b/x transposes at
@@ -27,7 +28,8 @@ namespace kb {
 
 struct LevelProg {
     int ntasks = 0, nlevels = 0;
-    int4* d_task = nullptr;   // per task: out, pivot slot (-1 none), first pair, plen | kind << 24
+    int4* d_task = nullptr;   // per task 2 x int4: {out, pivot slot (-1 none), index of 2nd pair, plen | kind << 24}
+                              //                       {a0, b0 (first operand pair, inline), -, -}
     int2* d_pair = nullptr;   // operand slots
     int* d_level_ptr = nullptr;
     int max_level_tasks = 0;
@@ -42,14 +44,15 @@ struct LevelProg {
         ntasks = static_cast<int>(tp.tasks.size());
         nlevels = tp.nlevels;
         n_mac = tp.n_mac;
-        std::vector<int4> rec(std::max(ntasks, 1));
+        std::vector<int4> rec(2 * static_cast<size_t>(std::max(ntasks, 1)));
         for (int t = 0; t < ntasks; ++t) {
             const Task& k = tp.tasks[t];
             if (k.plen >= (1 << 24)) {
                 err = "dot product too long for the level program";
                 return false;
             }
-            rec[t] = make_int4(k.out, k.div, k.pbeg, k.plen | (static_cast<int>(k.kind) << 24));
+            rec[2 * t] = make_int4(k.out, k.div, k.pbeg + 1, k.plen | (static_cast<int>(k.kind) << 24));
+            rec[2 * t + 1] = k.plen ? make_int4(tp.pa[k.pbeg], tp.pb[k.pbeg], 0, 0) : make_int4(0, 0, 0, 0);
         }
         std::vector<int2> pr(std::max<size_t>(tp.pa.size(), 1));
         for (size_t q = 0; q < tp.pa.size(); ++q) pr[q] = make_int2(tp.pa[q], tp.pb[q]);
@@ -85,20 +88,6 @@ struct LevelCall {
     long long lpad = 0;
     cudaStream_t st = nullptr;
 };
-
-// ---- grid-wide barrier for the persistent kernels (cooperative launch) ----
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned nblocks, unsigned& target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += nblocks;
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
 
 // scatter Ax[m][e] -> V[slot][sys]; V has been zeroed
 template <typename T>
@@ -162,97 +151,109 @@ struct LvArgs {
     const int4* task;
     const int2* pair;
     const int* level_ptr;
-    int nlevels, n_val, L, r;
-    long long lpad, Q;   // Q = L * r right-hand-side columns in the solve
+    int nlevels, n_val, r, slice;   // slice: batch columns owned by one CTA
+    long long L, lpad, Q;           // Q = L * r right-hand-side columns in the solve
     void* V;
     void* X;
     const int* sysidx;
-    unsigned* barrier;
     int* bad;                       // [L] OR of singular pivots
     unsigned long long* growth2;    // [L] max |L|^2 as ordered bits
 };
 
-// Persistent refactorization: thread per (task, system) inside a level.
+// Refactorization: thread per (task, system) inside a level, CTA per slice of systems.
 template <typename T>
 __global__ void __launch_bounds__(1024) lv_factor(const LvArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
     V_t* V = static_cast<V_t*>(a.V);
-    unsigned target = 0;
-    const int lanes = (a.L + 31) & ~31;  // systems padded to warps
-    for (int l = 0; l < a.nlevels; ++l) {
-        const int tb = __ldg(a.level_ptr + l), te = __ldg(a.level_ptr + l + 1);
-        const long long items = (long long)(te - tb) * lanes;
-        for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-             it += (long long)gridDim.x * blockDim.x) {
-            const int t = tb + static_cast<int>(it / lanes), m = static_cast<int>(it % lanes);
-            if (m >= a.L) continue;
-            const int sm = a.sysidx ? a.sysidx[m] : m;
-            const int4 rec = __ldg(a.task + t);
-            const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
-            const int2* pr = a.pair + rec.z;
-            V_t* o = V + (long long)rec.x * a.lpad + sm;
-            const V_t o0 = __ldcg(o);
-            V_t acc = S::zero();
+    // Systems never interact, so a CTA owns a slice of the batch axis and walks ALL levels on
+    // it alone: the barrier between levels is __syncthreads(), not a grid-wide barrier, and a
+    // CTA only ever reads values it wrote itself (same SM, coherent L1).
+    for (long long s0 = (long long)blockIdx.x * a.slice; s0 < a.L; s0 += (long long)gridDim.x * a.slice) {
+        const int ncol = static_cast<int>(min((long long)a.slice, a.L - s0));
+        int te = __ldg(a.level_ptr);
+        for (int l = 0; l < a.nlevels; ++l) {
+            const int tb = te;
+            te = __ldg(a.level_ptr + l + 1);
+            const int items = (te - tb) * ncol;
+            for (int it = threadIdx.x; it < items; it += blockDim.x) {
+                const int tq = it / ncol;
+                const int t = tb + tq, m = static_cast<int>(s0) + (it - tq * ncol);
+                const int sm = a.sysidx ? a.sysidx[m] : m;
+                const int4 rec = __ldg(a.task + 2 * t), first = __ldg(a.task + 2 * t + 1);
+                const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
+                const int2* pr = a.pair + rec.z;
+                V_t* o = V + (long long)rec.x * a.lpad + sm;
+                const V_t o0 = *o;
+                V_t acc = S::zero();
+                if (plen) S::fma_acc(acc, V[(long long)first.x * a.lpad + sm], V[(long long)first.y * a.lpad + sm]);
 #pragma unroll 4
-            for (int p = 0; p < plen; ++p) {
-                const int2 ab = __ldg(pr + p);
-                const V_t x = __ldcg(V + (long long)ab.x * a.lpad + sm);
-                const V_t y = __ldcg(V + (long long)ab.y * a.lpad + sm);
-                S::fma_acc(acc, x, y);
+                for (int p = 0; p < plen - 1; ++p) {
+                    const int2 ab = __ldg(pr + p);
+                    const V_t x = V[(long long)ab.x * a.lpad + sm];
+                    const V_t y = V[(long long)ab.y * a.lpad + sm];
+                    S::fma_acc(acc, x, y);
+                }
+                V_t v = S::sub(o0, acc);
+                if (kind == TK_RECIP) {
+                    if (S::bad_pivot(v)) a.bad[m] = 1;
+                    v = S::recip(v);
+                } else if (kind >= TK_MUL) {
+                    v = S::mul(v, V[(long long)rec.y * a.lpad + sm]);
+                    if (kind == TK_MUL_TRACK)
+                        atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v)));
+                }
+                *o = v;
             }
-            V_t v = S::sub(o0, acc);
-            if (kind == TK_RECIP) {
-                if (S::bad_pivot(v)) a.bad[m] = 1;
-                v = S::recip(v);
-            } else if (kind >= TK_MUL) {
-                v = S::mul(v, __ldcg(V + (long long)rec.y * a.lpad + sm));
-                if (kind == TK_MUL_TRACK)
-                    atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v)));
-            }
-            *o = v;
+            __syncthreads();
         }
-        if (l + 1 < a.nlevels) grid_barrier(a.barrier, gridDim.x, target);
     }
 }
 
-// Persistent triangular solves: thread per (task, right-hand-side column).
+// Triangular solves: thread per (task, right-hand-side column), CTA per slice of columns.
 template <typename T>
 __global__ void __launch_bounds__(1024) lv_solve(const LvArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
     const V_t* V = static_cast<const V_t*>(a.V);
     V_t* X = static_cast<V_t*>(a.X);
-    unsigned target = 0;
-    const long long lanes = (a.Q + 31) & ~31LL;
-    for (int l = 0; l < a.nlevels; ++l) {
-        const int tb = __ldg(a.level_ptr + l), te = __ldg(a.level_ptr + l + 1);
-        const long long items = (long long)(te - tb) * lanes;
-        for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-             it += (long long)gridDim.x * blockDim.x) {
-            const int t = tb + static_cast<int>(it / lanes);
-            const long long q = it % lanes;
-            if (q >= a.Q) continue;
-            const int m = static_cast<int>(q / a.r);
-            const int sm = a.sysidx ? a.sysidx[m] : m;
-            const int4 rec = __ldg(a.task + t);
-            const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
-            const int2* pr = a.pair + rec.z;
-            V_t* o = X + (long long)(rec.x - a.n_val) * a.Q + q;
-            const V_t o0 = __ldcg(o);
-            V_t acc = S::zero();
+    // Right-hand-side columns (system m, column c: q = m*r + c) never interact either: a CTA
+    // owns a slice of q and walks all levels on it, __syncthreads() between levels.
+    for (long long s0 = (long long)blockIdx.x * a.slice; s0 < a.Q; s0 += (long long)gridDim.x * a.slice) {
+        const int ncol = static_cast<int>(min((long long)a.slice, a.Q - s0));
+        int te = __ldg(a.level_ptr);
+        for (int l = 0; l < a.nlevels; ++l) {
+            const int tb = te;
+            te = __ldg(a.level_ptr + l + 1);
+            const long long items = (long long)(te - tb) * ncol;
+            for (long long it = threadIdx.x; it < items; it += blockDim.x) {
+                const int tq = static_cast<int>(it / ncol);
+                const int t = tb + tq;
+                const long long q = s0 + (it - (long long)tq * ncol);
+                const int m = static_cast<int>(q / a.r);
+                const int sm = a.sysidx ? a.sysidx[m] : m;
+                const int4 rec = __ldg(a.task + 2 * t), first = __ldg(a.task + 2 * t + 1);
+                const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
+                const int2* pr = a.pair + rec.z;
+                V_t* o = X + (long long)(rec.x - a.n_val) * a.Q + q;
+                const V_t o0 = *o;
+                V_t acc = S::zero();
+                if (plen)
+                    S::fma_acc(acc, __ldg(V + (long long)first.x * a.lpad + sm),
+                               X[(long long)(first.y - a.n_val) * a.Q + q]);
 #pragma unroll 4
-            for (int p = 0; p < plen; ++p) {
-                const int2 ab = __ldg(pr + p);
-                const V_t lu = __ldg(V + (long long)ab.x * a.lpad + sm);
-                const V_t xv = __ldcg(X + (long long)(ab.y - a.n_val) * a.Q + q);
-                S::fma_acc(acc, lu, xv);
+                for (int p = 0; p < plen - 1; ++p) {
+                    const int2 ab = __ldg(pr + p);
+                    const V_t lu = __ldg(V + (long long)ab.x * a.lpad + sm);
+                    const V_t xv = X[(long long)(ab.y - a.n_val) * a.Q + q];
+                    S::fma_acc(acc, lu, xv);
+                }
+                V_t v = S::sub(o0, acc);
+                if (kind >= TK_MUL) v = S::mul(v, __ldg(V + (long long)rec.y * a.lpad + sm));
+                *o = v;
             }
-            V_t v = S::sub(o0, acc);
-            if (kind >= TK_MUL) v = S::mul(v, __ldg(V + (long long)rec.y * a.lpad + sm));
-            *o = v;
+            __syncthreads();
         }
-        if (l + 1 < a.nlevels) grid_barrier(a.barrier, gridDim.x, target);
     }
 }
 
@@ -305,6 +306,16 @@ __global__ void lv_finish_status(int L, const int* __restrict__ bad,
     if (growth) growth[m] = sqrt(__longlong_as_double((long long)growth2[m]));
 }
 
+// Batch columns per CTA: one column each while the batch is smaller than the machine
+// (latency-bound: maximise the number of independent CTAs), else full warps of columns.
+static int pick_slice(long long ncols, int num_sms) {
+    if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_SLICE")) return std::max(1, std::atoi(e));
+    if (ncols <= num_sms) return 1;
+    const long long per = (ncols + num_sms - 1) / num_sms;
+    if (per < 32) return static_cast<int>(per);
+    return static_cast<int>(std::min<long long>(1024, (per + 31) / 32 * 32));
+}
+
 template <typename T>
 static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::string& err) {
     using V_t = typename Sc<T>::V;
@@ -344,11 +355,9 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
         cleanup();
         return KLU_OUT_OF_MEMORY;
     }
-    unsigned* barrier = static_cast<unsigned*>(tmpAux);
     unsigned long long* growth2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(tmpAux) + 64);
     int* bad = reinterpret_cast<int*>(growth2 + c.L);
 
-    int blocks_per_sm = 0;
     const bool factor = (pf != nullptr);
     if (factor) {
         const long long tot = (long long)c.n_val * c.L;
@@ -363,20 +372,10 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
         LvArgs a;
         a.task = pf->d_task; a.pair = pf->d_pair; a.level_ptr = pf->d_level_ptr;
         a.nlevels = pf->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = 1; a.lpad = lpad; a.Q = c.L;
-        a.V = V; a.X = nullptr; a.sysidx = c.sysidx; a.barrier = barrier; a.bad = bad; a.growth2 = growth2;
-        if (!chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, lv_factor<T>, 1024, 0), "occupancy")) {
-            cleanup();
-            return KLU_OUT_OF_MEMORY;
-        }
-        const long long avg_items = (long long)pf->ntasks * ((c.L + 31) & ~31) / std::max(1, pf->nlevels);
-        int grid = static_cast<int>(std::min<long long>((long long)blocks_per_sm * c.num_sms,
-                                                        std::max<long long>(1, (2 * avg_items + 1023) / 1024)));
-        void* args[] = {&a};
-        if (!chk(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lv_factor<T>), dim3(grid), dim3(1024),
-                                             args, 0, c.st), "launch lv_factor")) {
-            cleanup();
-            return KLU_OUT_OF_MEMORY;
-        }
+        a.V = V; a.X = nullptr; a.sysidx = c.sysidx; a.bad = bad; a.growth2 = growth2;
+        a.slice = pick_slice(c.L, c.num_sms);
+        const int grid = static_cast<int>(std::min<long long>((c.L + a.slice - 1) / a.slice, 2LL * c.num_sms));
+        lv_factor<T><<<grid, 1024, 0, c.st>>>(a);
         lv_finish_status<<<(c.L + 255) / 256, 256, 0, c.st>>>(c.L, bad, growth2, c.pattern_bad,
                                                             c.status, c.growth);
     }
@@ -395,20 +394,10 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
         LvArgs a;
         a.task = ps->d_task; a.pair = ps->d_pair; a.level_ptr = ps->d_level_ptr;
         a.nlevels = ps->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = c.r; a.lpad = lpad; a.Q = Q;
-        a.V = V; a.X = X; a.sysidx = c.sysidx; a.barrier = barrier + 8; a.bad = bad; a.growth2 = growth2;
-        if (!chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, lv_solve<T>, 1024, 0), "occupancy")) {
-            cleanup();
-            return KLU_OUT_OF_MEMORY;
-        }
-        const long long avg_items = (long long)ps->ntasks * ((Q + 31) & ~31LL) / std::max(1, ps->nlevels);
-        int grid = static_cast<int>(std::min<long long>((long long)blocks_per_sm * c.num_sms,
-                                                        std::max<long long>(1, (2 * avg_items + 1023) / 1024)));
-        void* args[] = {&a};
-        if (!chk(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lv_solve<T>), dim3(grid), dim3(1024),
-                                             args, 0, c.st), "launch lv_solve")) {
-            cleanup();
-            return KLU_OUT_OF_MEMORY;
-        }
+        a.V = V; a.X = X; a.sysidx = c.sysidx; a.bad = bad; a.growth2 = growth2;
+        a.slice = pick_slice(Q, c.num_sms);
+        const int grid = static_cast<int>(std::min<long long>((Q + a.slice - 1) / a.slice, 2LL * c.num_sms));
+        lv_solve<T><<<grid, 1024, 0, c.st>>>(a);
         lv_store_x<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
             c.L, c.n, c.r, static_cast<V_t*>(c.x), tr ? c.pnum : c.q, tr ? 1 : 0, Rs, lpad, c.sysidx, X);
     }

@@ -256,19 +256,24 @@ static int get_small_prog(Symbolic* S, int cx, int mode, int rc, SmallProg** out
     return 0;
 }
 
-static int get_level_prog(Symbolic* S, int cx, int mode, LevelProg** out) {
+static int get_level_prog(Symbolic* S, int cx, int mode, long long batch_cols, LevelProg** out) {
     Seeded& sd = S->seeded[cx];
-    auto key = std::make_pair(mode, 1);
+    // Task granularity (plan.cpp: Leveler): with few batch columns the time per level is one
+    // memory round trip, so every multiply-add is applied as soon as its operands are final
+    // (split 2: cfg 4 refactor+solves 193 -> 40 ms per step); with thousands of columns the
+    // kernels are traffic-bound and partial updates are grouped (>= 8 multiply-adds, split 3)
+    // or not split at all for the factorization (split 0).  Huge factorizations (cfg 3:
+    // 2.6e8 multiply-adds) always keep the dot form: one task per multiply-add would not fit.
+    int split;
+    if (mode == PM_FACTOR)
+        split = (sd.lay.n_lu >= 4000000 || batch_cols >= 2048) ? 0 : 2;
+    else
+        split = batch_cols >= 4096 ? 3 : 2;
+    if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_SPLIT")) split = std::atoi(e);
+    auto key = std::make_pair(mode, split);
     auto it = sd.level.find(key);
     if (it == sd.level.end()) {
         TaskProgram tp;
-        // level regime: one thread per (task, system); short partial updates keep the time per
-        // level at one L2 round trip.  Huge factorizations (cfg 3: 2.6e8 multiply-adds) keep
-        // the dot form: one task per multiply-add group would not fit.
-        // (measured: cfg 4 refactor 193 -> 69 ms with per-level partial updates; the multi-RHS
-        // solve of cfg 3 prefers groups of >= 8 multiply-adds: fewer read-modify-writes of X)
-        int split = (mode == PM_FACTOR) ? (sd.lay.n_lu >= 4000000 ? 0 : 2) : 3;
-        if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_SPLIT")) split = std::atoi(e);
         build_program(S->ord, sd.piv, sd.lay, mode, 1, tp, split);
         auto lp = std::make_unique<LevelProg>();
         std::string err;
@@ -454,12 +459,12 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
     }
     LevelProg *pf = nullptr, *ps = nullptr;
     if (factor) {
-        int e = get_level_prog(S, cx, PM_FACTOR, &pf);
+        int e = get_level_prog(S, cx, PM_FACTOR, op.L, &pf);
         if (e) return e;
     }
     if (op.mode != PM_FACTOR) {
         const bool tr = (op.mode == PM_FACTOR_TSOLVE || op.mode == PM_TSOLVE);
-        int e = get_level_prog(S, cx, tr ? PM_TSOLVE : PM_SOLVE, &ps);
+        int e = get_level_prog(S, cx, tr ? PM_TSOLVE : PM_SOLVE, static_cast<long long>(op.L) * op.r, &ps);
         if (e) return e;
     }
     std::string err;
