@@ -213,6 +213,7 @@ __device__ __forceinline__ void run_chunk(const SmallArgs& a, int pi, int b0, in
         V_t* po = slot_hi<T>(Vb, h);
         const V_t vo = *po;
         typename S::Acc c = S::acc0();
+#pragma unroll 1
         do {
             const uint32_t w0 = ops[0], w1 = ops[32];
             ops += 64;
@@ -342,8 +343,18 @@ __global__ void __launch_bounds__(544, 1) small_kernel(const __grid_constant__ S
                 // max-abs row scaling (KLU scale = 2): Rs in original row order
                 for (int i = lane; i < n; i += 32) {
                     const int pb = __ldg(a.rs_ptr + i), pe = __ldg(a.rs_ptr + i + 1);
-                    double mx = 0.0;
-                    for (int p = pb; p < pe; ++p) mx = fmax(mx, S::mag(S::ld(V + __ldg(a.rs_slot + p))));
+                    // |z| = sqrt(re^2 + im^2) from the largest squared modulus of the row; the
+                    // overflow-safe hypot form (what KLU uses) only when a square leaves the
+                    // safe range
+                    double q2 = 0.0;
+                    for (int p = pb; p < pe; ++p) q2 = fmax(q2, S::mag2(S::ld(V + __ldg(a.rs_slot + p))));
+                    double mx;
+                    if (q2 > 1e-200 && q2 < 1e200) {
+                        mx = sqrt(q2);
+                    } else {
+                        mx = 0.0;
+                        for (int p = pb; p < pe; ++p) mx = fmax(mx, S::mag(S::ld(V + __ldg(a.rs_slot + p))));
+                    }
                     if (mx == 0.0) mx = 1.0;
                     Rs[i] = mx;
                     for (int p = pb; p < pe; ++p) {
