@@ -32,6 +32,7 @@ struct Sc<double> {
     __device__ static __forceinline__ V add(V a, V b) { return a + b; }
     __device__ static __forceinline__ V mul(V a, V b) { return a * b; }
     __device__ static __forceinline__ V recip(V a) { return 1.0 / a; }
+    __device__ static __forceinline__ V fast_recip(V a) { return __drcp_rn(a); }
     __device__ static __forceinline__ V rdiv(V a, double s) { return a / s; }
     __device__ static __forceinline__ double mag(V a) { return fabs(a); }
     __device__ static __forceinline__ double mag2(V a) { return a * a; }
@@ -76,6 +77,15 @@ struct Sc<zc> {
         const double r = a.x / a.y, den = r * a.x + a.y;
         return make_double2(r / den, -1.0 / den);
     }
+    // conj(a) / |a|^2 with one reciprocal; Smith's form outside the range where |a|^2 is safe
+    __device__ static __forceinline__ V fast_recip(V a) {
+        const double m = fma(a.x, a.x, a.y * a.y);
+        if (m > 1e-280 && m < 1e280) {
+            const double inv = __drcp_rn(m);
+            return make_double2(a.x * inv, -a.y * inv);
+        }
+        return recip(a);
+    }
     __device__ static __forceinline__ V rdiv(V a, double s) { return make_double2(a.x / s, a.y / s); }
     __device__ static __forceinline__ double mag(V a) { return hypot(a.x, a.y); }
     __device__ static __forceinline__ double mag2(V a) { return a.x * a.x + a.y * a.y; }
@@ -115,6 +125,7 @@ struct SmallArgs {
     // [1] further right-hand-side chunks (solve only)
     const uint32_t* stream[2];
     int nchunks[2];
+    int nbatch[2];                          // batches (one-warp form) / levels (multi-warp form)
     uint32_t ctrl[2][kMaxBatches];          // warp-uniform control words (constant bank)
     uint16_t chunk_ptr[2][kMaxChunks + 1];  // first batch of each chunk
     int W;                   // systems (= consumer warps) per CTA

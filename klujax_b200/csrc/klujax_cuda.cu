@@ -22,6 +22,7 @@
 #include "symbolic.hpp"
 #include "kernels_small.cuh"
 #include "kernels_level.cuh"
+#include "kernels_wide.cuh"
 
 namespace kb {
 
@@ -81,7 +82,7 @@ struct Seeded {
     SlotLayout lay;
     int regime = 0;  // 0 = shared-memory warp-per-system, 1 = level-scheduled global
     DevBuf d_colptr, d_srow, d_sslot, d_rs_ptr, d_rs_slot, d_pnum, d_q;
-    std::map<std::pair<int, int>, std::unique_ptr<SmallProg>> small;
+    std::map<std::pair<int, int>, std::unique_ptr<SmallProg>> small;  // key (mode, rc + 1000 * wide)
     std::map<std::pair<int, int>, std::unique_ptr<LevelProg>> level;
     int64_t info_levels = 0, info_mac = 0, info_nbatch = 0, info_stream_words = 0;
 };
@@ -229,17 +230,21 @@ static int ensure_seeded_dev(Symbolic* S, int cx, int nz, const int32_t* Ai_dev,
 // ---------------------------------------------------------------------------
 // program caches
 // ---------------------------------------------------------------------------
-static int get_small_prog(Symbolic* S, int cx, int mode, int rc, SmallProg** out) {
+static int get_small_prog(Symbolic* S, int cx, int mode, int rc, bool wide, SmallProg** out) {
     Seeded& sd = S->seeded[cx];
-    auto key = std::make_pair(mode, rc);
+    auto key = std::make_pair(mode, rc + (wide ? 1000 : 0));
     auto it = sd.small.find(key);
     if (it == sd.small.end()) {
         TaskProgram tp;
         PackedProgram pp;
         int split = 0;  // measured: the dot form beats as-soon-as-possible solve updates here (220k vs 234k cycles)
         if (const char* e = std::getenv("KLUJAX_CUDA_SPLIT")) split = std::atoi(e);
+        if (wide) {
+            split = 111;  // one multiply-add per partial update (measured best: 11 < 14 < 24 < 47)
+            if (const char* e = std::getenv("KLUJAX_CUDA_WIDE_GROUP")) split = 100 + std::atoi(e);
+        }
         build_program(S->ord, sd.piv, sd.lay, mode, rc, tp, split);
-        if (!pack_program(sd.lay, tp, pp)) return fail(KLU_TOO_LARGE, "program does not fit the shared-memory regime");
+        if (!(wide ? pack_program_wide(sd.lay, tp, pp) : pack_program(sd.lay, tp, pp))) return fail(KLU_TOO_LARGE, "program does not fit the shared-memory regime");
         auto sp = std::make_unique<SmallProg>();
         CUDA_OK(sp->stream.upload(pp.stream));
         sp->nchunks = pp.nchunks;
@@ -322,21 +327,35 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
         }
         if (rc < 1) return fail(KLU_TOO_LARGE, "system does not fit the shared-memory regime");
     }
-    int e = get_small_prog(S, cx, op.mode, rc, &p0);
+    // Two shared-memory kernels: one warp per system (kernels_small.cuh) or four warps per
+    // system (kernels_wide.cuh).  The latter shortens the dependent chain of a system and wins
+    // when shared memory holds few systems per SM (cfg 5: 5 systems, 8.2 vs 10.7 ms); with many
+    // small systems per SM the one-warp form keeps more of them in flight (cfg 2: 15 systems,
+    // 0.15 vs 0.29 ms).
+    bool wide;
+    {
+        const size_t slots = static_cast<size_t>(sd.lay.n_val) + static_cast<size_t>(n) * rc + 3;
+        const size_t fit = (kMaxDynSmem - kSmallHeaderBytes) / (slots * vsz + n * 8ull + 16);
+        wide = fit <= 8;
+        if (const char* ev = std::getenv("KLUJAX_CUDA_WIDE")) wide = std::atoi(ev) != 0;
+    }
+    int e = get_small_prog(S, cx, op.mode, rc, wide, &p0);
     if (e) return e;
     if (solve && op.r > rc) {
-        e = get_small_prog(S, cx, transpose ? PM_TSOLVE : PM_SOLVE, rc, &p1);
+        e = get_small_prog(S, cx, transpose ? PM_TSOLVE : PM_SOLVE, rc, wide, &p1);
         if (e) return e;
     }
     static thread_local SmallArgs a;  // ~14 KB of parameters: control words travel by value
     std::memset(&a, 0, sizeof(a));
     a.stream[0] = p0->stream.as<uint32_t>();
     a.nchunks[0] = p0->nchunks;
+    a.nbatch[0] = p0->nbatch;
     std::copy(p0->ctrl.begin(), p0->ctrl.end(), a.ctrl[0]);
     std::copy(p0->chunk_ptr.begin(), p0->chunk_ptr.end(), a.chunk_ptr[0]);
     if (p1) {
         a.stream[1] = p1->stream.as<uint32_t>();
         a.nchunks[1] = p1->nchunks;
+        a.nbatch[1] = p1->nbatch;
         std::copy(p1->ctrl.begin(), p1->ctrl.end(), a.ctrl[1]);
         std::copy(p1->chunk_ptr.begin(), p1->chunk_ptr.end(), a.chunk_ptr[1]);
     }
@@ -369,18 +388,20 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     a.status = op.status;
     a.growth = op.growth;
     a.L = op.L;
-    // CTA = W systems (one consumer warp each) + the producer warp + the schedule ring.
-    // W: as many value arrays as fit next to the ring, but enough CTAs to cover the SMs.
-    const size_t per_sys = (static_cast<size_t>(a.n_slots) * vsz + n * 8ull + 15) & ~size_t(15);
-    int W = static_cast<int>(std::min<size_t>(16, (kMaxDynSmem - kSmallHeaderBytes) / per_sys));
+    // CTA = W systems + the producer warp + the schedule ring.  One-warp form: one consumer warp
+    // per system, as many systems as fit.  Multi-warp form: kWarpsPerSystem warps per system,
+    // at most 5 systems per CTA (thread limit), several CTAs per SM when systems are small.
+    const size_t per_sys = wide ? ((static_cast<size_t>(a.n_slots) * vsz + n * 8ull + 16 + 15) & ~size_t(15))
+                                : ((static_cast<size_t>(a.n_slots) * vsz + n * 8ull + 15) & ~size_t(15));
+    int W = static_cast<int>(std::min<size_t>(wide ? 5 : 16, (kMaxDynSmem - kSmallHeaderBytes) / per_sys));
     if (W < 1) return fail(KLU_TOO_LARGE, "system does not fit the shared-memory regime");
     const int sms = num_sms();
     while (W > 1 && (op.L + W - 1) / W < sms) --W;  // small batches: spread over all SMs first
     if (const char* fw = std::getenv("KLUJAX_CUDA_SMALL_W")) W = std::max(1, std::min(W, std::atoi(fw)));
     a.W = W;
     const size_t smem = kSmallHeaderBytes + per_sys * W;
-    const int threads = 32 * (W + 1);
-    auto kern = small_kernel<T>;
+    const int threads = wide ? 32 * (kWarpsPerSystem * W + 1) : 32 * (W + 1);
+    auto kern = wide ? wide_kernel<T> : small_kernel<T>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int occ = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));

@@ -117,7 +117,8 @@ struct Leveler {
     std::vector<int> val_level, read_level;
     TaskProgram& prog;
     bool split;
-    int min_group = 1;
+    bool single = false;
+    int min_group = 1, max_group = 0;
     std::vector<std::pair<int, int>> order;  // (ready level, pair index)
     Leveler(int nidx, TaskProgram& p, bool split_) : val_level(nidx, 0), read_level(nidx, 0), prog(p), split(split_) {}
 
@@ -160,8 +161,33 @@ struct Leveler {
         } else {
             std::stable_sort(order.begin(), order.end(),
                              [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first < y.first; });
+            if (single) {  // at most one multiply-add per destination and level
+                for (int q = 1; q < np; ++q) order[q].first = std::max(order[q].first, order[q - 1].first + 1);
+                if (np) last = std::max(last, order[np - 1].first);
+            }
         }
         int ob = 0;
+        if (max_group > 0 && split) {
+            // bounded groups (multi-warp shared-memory kernel): a partial update holds at most
+            // max_group multiply-adds; it is cut where the next pair only becomes ready at a
+            // later level (once min_group pairs are in), and a burst that is ready all at once
+            // is chained over consecutive levels.  The last group carries the finish.
+            int prev_level = 0;
+            while (ob < np) {
+                int oe = ob + 1;
+                while (oe < np && oe - ob < max_group &&
+                       (order[oe].first == order[oe - 1].first || oe - ob < min_group))
+                    ++oe;
+                const int lvl = std::max(order[oe - 1].first, prev_level + 1);
+                if (oe == np) {
+                    last = std::max(last, lvl);
+                    break;
+                }
+                emit(TK_SUB, out, -1, lvl, pairs, ob, oe);
+                prev_level = lvl;
+                ob = oe;
+            }
+        } else
         while (ob < np) {
             // a partial update takes every pair that is ready at one level, and keeps taking
             // later ones until it holds at least min_group pairs
@@ -196,6 +222,11 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
     // solves only, 2 = everywhere, 3 = everywhere in groups of at least 8 multiply-adds
     Leveler lv(lay.n_val + nx, prog, split >= 2);
     if (split == 3) lv.min_group = 8;
+    if (split == 4) lv.single = true;  // single multiply-add tasks
+    if (split >= 100) {                // 100 + 10*min + max: bounded groups (multi-warp shared-memory kernel)
+        lv.min_group = (split - 100) / 10;
+        lv.max_group = (split - 100) % 10;
+    }
     const std::vector<int> k1of = block_of_column(ord);
     auto xs = [&](int k, int c) { return lay.n_val + k * rc + c; };
     std::vector<std::pair<int, int>> pairs;
@@ -411,6 +442,64 @@ bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram&
     }
     out.chunk_ptr.push_back(static_cast<uint16_t>(out.nbatch));
     return out.nbatch <= kMaxBatches && out.nchunks <= kMaxChunks;
+}
+
+}  // namespace kb
+
+namespace kb {
+
+// Packs a bounded-group program (build_program with split = 100 + 10*min + max, max <= 7) for
+// the multi-warp shared-memory kernel (kernels_wide.cuh).  A level is cut into 128-lane steps;
+// a step is one header line (per lane: out<<18 | pivot-or-ONE<<4 | kind) and P operand lines
+// (per lane: a<<18 | b<<4, 0 = nothing), P = longest task of the step (tasks are sorted by
+// length).  ctrl[step] = P | level-ends<<4; steps never straddle a chunk.
+bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out) {
+    out = PackedProgram();
+    constexpr int LANES = 128;
+    const int nx = (prog.mode == PM_FACTOR) ? 0 : lay.n * prog.rc;
+    out.zero_slot = lay.n_val + nx;  // then ONE (= 1), then TRASH
+    out.n_slots = out.zero_slot + 3;
+    if (out.n_slots > 16383) return false;
+    const uint32_t ONE = out.zero_slot + 1;
+    size_t chunk_base = 0;
+    int used = kChunkWords;  // forces a first chunk
+    auto open_chunk = [&]() {
+        chunk_base = out.stream.size();
+        out.stream.resize(chunk_base + kChunkWords, 0u);
+        out.chunk_ptr.push_back(static_cast<uint16_t>(out.ctrl.size()));
+        used = 0;
+        out.nchunks++;
+    };
+    std::vector<int> order;
+    for (int l = 0; l < prog.nlevels; ++l) {
+        const int tb = prog.level_ptr[l], te = prog.level_ptr[l + 1];
+        order.resize(te - tb);
+        for (int t = tb; t < te; ++t) order[t - tb] = t;  // already sorted by length, longest first
+        for (size_t i = 0; i < order.size(); i += LANES) {
+            const size_t cnt = std::min<size_t>(LANES, order.size() - i);
+            const int P = prog.tasks[order[i]].plen;
+            if (P > 7) return false;
+            const int words = LANES * (1 + P);
+            if (used + words > kChunkWords) open_chunk();
+            uint32_t* base = out.stream.data() + chunk_base + used;
+            for (size_t k = 0; k < cnt; ++k) {
+                const Task& tk = prog.tasks[order[i + k]];
+                const uint32_t d = tk.div >= 0 ? static_cast<uint32_t>(tk.div) : ONE;
+                const uint32_t kind = tk.kind == TK_RECIP ? 4u : tk.kind == TK_MUL_TRACK ? 3u : tk.kind == TK_MUL ? 2u : 1u;
+                base[k] = (static_cast<uint32_t>(tk.out) << 18) | (d << 4) | kind;
+                for (int q = 0; q < tk.plen; ++q)
+                    base[LANES * (1 + q) + k] = (static_cast<uint32_t>(prog.pa[tk.pbeg + q]) << 18) |
+                                                (static_cast<uint32_t>(prog.pb[tk.pbeg + q]) << 4);
+            }
+            const bool level_end = (i + LANES >= order.size());
+            out.ctrl.push_back(static_cast<uint32_t>(P) | (level_end ? 16u : 0u));
+            used += words;
+            out.lines_used += 1 + P;
+        }
+    }
+    out.chunk_ptr.push_back(static_cast<uint16_t>(out.ctrl.size()));
+    out.nbatch = static_cast<int>(out.ctrl.size());
+    return out.nbatch > 0 && out.nbatch <= kMaxBatches && out.nchunks <= kMaxChunks;
 }
 
 }  // namespace kb

@@ -417,3 +417,35 @@ def test_free_semantics(K):
     num.close()
     assert K.free_symbolic(sym) == 0             # manager path returns 0 (klujax.py:251-253)
     assert K.free_symbolic(np.uint64(0)) == 0    # null handle: nothing to free
+
+
+@pytest.mark.parametrize("wide", ["0", "1"])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_both_shared_memory_kernels(K, oracle, wide, dtype, monkeypatch):
+    """One warp per system (kernels_small.cuh) and four warps per system (kernels_wide.cuh)
+    give the oracle's answers on the same inputs, for every entry point."""
+    monkeypatch.setenv("KLUJAX_CUDA_WIDE", wide)
+    Ai, Aj, Ax, b = synth.ref_style_case(40, 160, 7, 5, dtype)
+    so = oracle.analyze(Ai, Aj, 40)
+    xo = oracle.solve_with_symbol(Ai, Aj, Ax, b, so)
+    xto = oracle.solve_with_symbol(Ai, Aj, Ax, b, so, transpose=True)
+    with K.analyze(Ai, Aj, 40) as sym:
+        assert relerr(np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym)), xo) < X_TOL
+        assert relerr(np_(K.tsolve_with_symbol(Ai, Aj, Ax, b, sym)), xto) < X_TOL
+        st, gr = K.last_status()
+        assert int(st.abs().max()) == 0 and 0.0 < float(gr.max()) <= 1000.0
+        with K.factor(Ai, Aj, Ax, sym) as num:
+            assert relerr(np_(K.solve_with_numeric(num, b, sym)), xo) < X_TOL
+            assert relerr(np_(K.tsolve_with_numeric(num, b, sym)), xto) < X_TOL
+            x3, _ = K.refactor_and_solve(Ai, Aj, Ax * 2.0, b, num, sym)
+            assert relerr(np_(x3) * 2.0, xo) < X_TOL
+    oracle.free_symbolic(so)
+    if dtype is np.complex128:  # and on the cfg5 pattern
+        pat = synth.SaxPattern(128, seed=2)
+        Axs = pat.values(0, 12)
+        bs = np.random.default_rng(1).standard_normal((12, 128, 2)) + 0j
+        so = oracle.analyze(pat.Ai, pat.Aj, 128)
+        with K.analyze(pat.Ai, pat.Aj, 128) as sym:
+            assert relerr(np_(K.solve_with_symbol(pat.Ai, pat.Aj, Axs, bs, sym)),
+                          oracle.solve_with_symbol(pat.Ai, pat.Aj, Axs, bs, so)) < X_TOL
+        oracle.free_symbolic(so)
