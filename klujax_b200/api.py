@@ -220,20 +220,64 @@ def analyze(Ai: Any, Aj: Any, n_col: int) -> KLUHandleManager:
     return KLUHandleManager(np.uint64(h), free_symbolic, owner=True)
 
 
+_PIPELINE_MIN_SYSTEMS = 8192   # host-resident batches at least this large are streamed in chunks
+_PIPELINE_CHUNKS = 8
+_streams: dict = {}
+
+
+def _copy_streams(dev: torch.device):
+    if dev not in _streams:
+        _streams[dev] = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    return _streams[dev]
+
+
 def _solve_symbol(fn: str, Ai, Aj, Ax, b, symbolic, check: bool):
     Ai_t, Aj_t, Ax_t, b_t = _as_tensor(Ai), _as_tensor(Aj), _as_tensor(Ax), _as_tensor(b)
     _check_coo(Ai_t, Aj_t, Ax_t)
     Ax_t, b_t, shape = _canonical(Ax_t, b_t, "b")
     cx = _is_complex(Ax_t, b_t)
     Ai_d, Aj_d = _indices(Ai_t), _indices(Aj_t)
-    Ax_d, b_d = _values(Ax_t, cx), _values(b_t, cx)
-    L, n, r = b_d.shape
-    x = torch.empty_like(b_d)
-    st, gr = _new_status(L)
     sym = int(_handle_value(symbolic).reshape(-1)[0])
     f = getattr(_cabi.lib(), f"klujax_cuda_{fn}_{_suffix(cx)}")
-    _cabi.check(f(C.c_uint64(sym), L, n, r, Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d),
-                  _ptr(b_d), _ptr(x), _ptr(st), _ptr(gr), _stream()))
+    L, n, r = b_t.shape
+    nz = Ai_d.numel()
+    vdt = torch.complex128 if cx else torch.float64
+    host_batch = (not Ax_t.is_cuda and not b_t.is_cuda and L >= _PIPELINE_MIN_SYSTEMS
+                  and Ax_t.dtype == vdt and b_t.dtype == vdt
+                  and Ax_t.is_contiguous() and b_t.is_contiguous())
+    if not host_batch:
+        Ax_d, b_d = _values(Ax_t, cx), _values(b_t, cx)
+        x = torch.empty_like(b_d)
+        st, gr = _new_status(L)
+        _cabi.check(f(C.c_uint64(sym), L, n, r, nz, _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d),
+                      _ptr(b_d), _ptr(x), _ptr(st), _ptr(gr), _stream()))
+    else:
+        # Host-resident batch: systems are independent, so the batch is streamed in chunks on
+        # two streams - the host->device copy of chunk k+1 overlaps the kernels of chunk k.
+        dev = _device()
+        Ax_d = torch.empty((L, nz), dtype=vdt, device=dev)
+        b_d = torch.empty((L, n, r), dtype=vdt, device=dev)
+        x = torch.empty_like(b_d)
+        st, gr = _new_status(L)
+        cur = torch.cuda.current_stream()
+        streams = _copy_streams(dev)
+        bounds = [L * k // _PIPELINE_CHUNKS for k in range(_PIPELINE_CHUNKS + 1)]
+        for s in streams:
+            s.wait_stream(cur)
+        for k in range(_PIPELINE_CHUNKS):
+            lo, hi = bounds[k], bounds[k + 1]
+            s = streams[k % 2]
+            with torch.cuda.stream(s):
+                Ax_d[lo:hi].copy_(Ax_t[lo:hi], non_blocking=True)
+                b_d[lo:hi].copy_(b_t[lo:hi], non_blocking=True)
+                _cabi.check(f(C.c_uint64(sym), hi - lo, n, r, nz, _ptr(Ai_d), _ptr(Aj_d),
+                              _ptr(Ax_d[lo:hi]), _ptr(b_d[lo:hi]), _ptr(x[lo:hi]), _ptr(st[lo:hi]),
+                              _ptr(gr[lo:hi]), C.c_void_p(s.cuda_stream)))
+        for s in streams:
+            cur.wait_stream(s)
+        for t in (Ax_d, b_d, x, st, gr, Ai_d, Aj_d):
+            t.record_stream(streams[0])
+            t.record_stream(streams[1])
     _raise_if_failed(st, "klu_factor", check)
     return x.reshape(shape)
 

@@ -92,7 +92,13 @@ struct Symbolic {
     Ordering ord;
     std::vector<int> Ai, Aj;  // COO of the analyze call
     Seeded seeded[2];
-    DevBuf d_coo_dst, d_bad;
+    // per-stream scratch of the COO map (slot of every COO entry of the call + pattern flag):
+    // calls on different streams may overlap on the device
+    struct Scratch {
+        DevBuf coo_dst, bad;
+    };
+    std::map<cudaStream_t, std::unique_ptr<Scratch>> scratch;
+    Scratch* cur = nullptr;  // scratch of the call in flight (under mu)
     std::mutex mu;
 };
 
@@ -173,10 +179,6 @@ static int upload_seeded(Symbolic* S, int cx) {
     CUDA_OK(sd.d_rs_slot.upload(sd.lay.rs_slot));
     CUDA_OK(sd.d_pnum.upload(sd.piv.Pnum));
     CUDA_OK(sd.d_q.upload(S->ord.Q));
-    if (!S->d_coo_dst.p) {
-        CUDA_OK(S->d_coo_dst.alloc(sizeof(int) * (S->A.rowidx.size() + 1)));
-        CUDA_OK(S->d_bad.alloc(sizeof(int)));
-    }
     return 0;
 }
 
@@ -368,8 +370,8 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     a.flags = (factor ? SF_FACTOR : SF_LOAD_NUMERIC) | (solve ? SF_SOLVE : 0) |
               (op.store_numeric ? SF_STORE_NUMERIC : 0) |
               (solve ? (transpose ? SF_SCALE_OUT : SF_SCALE_IN) : 0);
-    a.coo_dst = S->d_coo_dst.as<int>();
-    a.pattern_bad = S->d_bad.as<int>();
+    a.coo_dst = S->cur->coo_dst.as<int>();
+    a.pattern_bad = S->cur->bad.as<int>();
     a.rs_ptr = sd.d_rs_ptr.as<int>();
     a.rs_slot = sd.d_rs_slot.as<int>();
     a.in_perm = transpose ? sd.d_q.as<int>() : sd.d_pnum.as<int>();
@@ -434,14 +436,24 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
     Seeded& sd = S->seeded[cx];
     const bool factor = op.mode <= PM_FACTOR_TSOLVE;
     if (op.L <= 0) return 0;
+    {
+        auto& slot = S->scratch[op.st];
+        if (!slot) {
+            slot = std::make_unique<Symbolic::Scratch>();
+            CUDA_OK(slot->coo_dst.alloc(sizeof(int) * (S->A.rowidx.size() + 1)));
+            CUDA_OK(slot->bad.alloc(sizeof(int)));
+            CUDA_OK(cudaMemset(slot->bad.p, 0, sizeof(int)));
+        }
+        S->cur = slot.get();
+    }
     if (factor) {
         int e = ensure_seeded_dev(S, cx, op.nz, op.Ai, op.Aj, op.Ax, op.st);
         if (e) return e;
-        CUDA_OK(cudaMemsetAsync(S->d_bad.p, 0, sizeof(int), op.st));
+        CUDA_OK(cudaMemsetAsync(S->cur->bad.p, 0, sizeof(int), op.st));
         const int nz = op.nz;
         coo_map_kernel<<<(nz + 255) / 256, 256, 0, op.st>>>(
             nz, sd.lay.n, op.Ai, op.Aj, sd.d_colptr.as<int>(), sd.d_srow.as<int>(),
-            sd.d_sslot.as<int>(), S->d_coo_dst.as<int>(), S->d_bad.as<int>());
+            sd.d_sslot.as<int>(), S->cur->coo_dst.as<int>(), S->cur->bad.as<int>());
         CUDA_OK(cudaGetLastError());
     } else if (!sd.ok) {
         return fail(KLU_INVALID, "numeric handle without a factorization");
@@ -458,8 +470,8 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
     lc.b = op.b;
     lc.b_stride = op.b_stride;
     lc.x = op.x;
-    lc.coo_dst = S->d_coo_dst.as<int>();
-    lc.pattern_bad = S->d_bad.as<int>();
+    lc.coo_dst = S->cur->coo_dst.as<int>();
+    lc.pattern_bad = S->cur->bad.as<int>();
     lc.rs_ptr = sd.d_rs_ptr.as<int>();
     lc.rs_slot = sd.d_rs_slot.as<int>();
     lc.pnum = sd.d_pnum.as<int>();
