@@ -158,12 +158,16 @@ static int seed_from_csc_values(Symbolic* S, int cx, const T* csc_values) {
     }
     if (const char* force = std::getenv("KLUJAX_CUDA_FORCE_REGIME")) sd.regime = std::atoi(force) ? 1 : 0;
     {
-        TaskProgram tf;
-        if (sd.regime == 0 || sd.lay.n_lu < 4000000) {
-            build_program(S->ord, sd.piv, sd.lay, PM_FACTOR, 0, tf);
-            sd.info_mac = tf.n_mac;
-            if (sd.regime == 1) sd.info_levels = tf.nlevels;
-        }
+        // multiply-adds of one refactorization: every U(j,k) meets the whole column L(:,j)
+        const SlotLayout& lay = sd.lay;
+        int64_t mac = 0;
+        for (int k = 0; k < lay.n; ++k)
+            for (int su = lay.col_begin[k]; su < lay.diag_slot[k]; ++su) {
+                const int j = lay.slot_row[su];
+                mac += lay.col_begin[j + 1] - lay.diag_slot[j] - 1;
+            }
+        sd.info_mac = mac;
+        if (sd.regime == 1) sd.info_levels = -1;  // known once the level program is built
     }
     sd.ok = true;
     return 0;
@@ -285,6 +289,7 @@ static int get_level_prog(Symbolic* S, int cx, int mode, long long batch_cols, L
         auto lp = std::make_unique<LevelProg>();
         std::string err;
         if (!lp->upload(sd.lay, tp, err)) return fail(KLU_OUT_OF_MEMORY, err);
+        if (mode == PM_FACTOR) sd.info_levels = tp.nlevels;
         it = sd.level.emplace(key, std::move(lp)).first;
     }
     *out = it->second.get();
