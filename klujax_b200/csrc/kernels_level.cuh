@@ -171,16 +171,33 @@ __global__ void __launch_bounds__(1024) lv_factor(const LvArgs a) {
     // CTA only ever reads values it wrote itself (same SM, coherent L1).
     for (long long s0 = (long long)blockIdx.x * a.slice; s0 < a.L; s0 += (long long)gridDim.x * a.slice) {
         const int ncol = static_cast<int>(min((long long)a.slice, a.L - s0));
-        int te = __ldg(a.level_ptr);
+        // The task record of a thread's first item of the NEXT level is fetched before the
+        // barrier, so a level costs one memory round trip (the operands), not two.
+        int te = __ldg(a.level_ptr), te_next = __ldg(a.level_ptr + 1);
+        int4 pre_rec = make_int4(0, 0, 0, 0), pre_first = pre_rec;
+        if (static_cast<int>(threadIdx.x) < (te_next - te) * ncol) {
+            const int t0 = te + static_cast<int>(threadIdx.x) / ncol;
+            pre_rec = __ldg(a.task + 2 * t0);
+            pre_first = __ldg(a.task + 2 * t0 + 1);
+        }
         for (int l = 0; l < a.nlevels; ++l) {
             const int tb = te;
-            te = __ldg(a.level_ptr + l + 1);
+            te = te_next;
+            te_next = (l + 1 < a.nlevels) ? __ldg(a.level_ptr + l + 2) : te;
             const int items = (te - tb) * ncol;
+            const int4 cur_rec = pre_rec, cur_first = pre_first;
+            if (static_cast<int>(threadIdx.x) < (te_next - te) * ncol) {
+                const int t1 = te + static_cast<int>(threadIdx.x) / ncol;
+                pre_rec = __ldg(a.task + 2 * t1);
+                pre_first = __ldg(a.task + 2 * t1 + 1);
+            }
             for (int it = threadIdx.x; it < items; it += blockDim.x) {
                 const int tq = it / ncol;
                 const int t = tb + tq, m = static_cast<int>(s0) + (it - tq * ncol);
                 const int sm = a.sysidx ? a.sysidx[m] : m;
-                const int4 rec = __ldg(a.task + 2 * t), first = __ldg(a.task + 2 * t + 1);
+                const bool pre = it == static_cast<int>(threadIdx.x);
+                const int4 rec = pre ? cur_rec : __ldg(a.task + 2 * t);
+                const int4 first = pre ? cur_first : __ldg(a.task + 2 * t + 1);
                 const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
                 const int2* pr = a.pair + rec.z;
                 V_t* o = V + (long long)rec.x * a.lpad + sm;
@@ -221,6 +238,8 @@ __global__ void __launch_bounds__(1024) lv_solve(const LvArgs a) {
     // owns a slice of q and walks all levels on it, __syncthreads() between levels.
     for (long long s0 = (long long)blockIdx.x * a.slice; s0 < a.Q; s0 += (long long)gridDim.x * a.slice) {
         const int ncol = static_cast<int>(min((long long)a.slice, a.Q - s0));
+        // (no record prefetch here: measured 3x slower on the multi-RHS solve of cfg 3, where a
+        // thread runs many items per level and the extra live registers cost more than they save)
         int te = __ldg(a.level_ptr);
         for (int l = 0; l < a.nlevels; ++l) {
             const int tb = te;
@@ -313,7 +332,9 @@ static int pick_slice(long long ncols, int num_sms) {
     if (ncols <= num_sms) return 1;
     const long long per = (ncols + num_sms - 1) / num_sms;
     if (per < 32) return static_cast<int>(per);
-    return static_cast<int>(std::min<long long>(1024, (per + 31) / 32 * 32));
+    // 64 columns per CTA: measured best on the multi-RHS solve of cfg 3 (273 ms vs 288 at 32 and
+    // 369 at 128) - narrower slices keep more rows of X of a CTA in L1/L2
+    return static_cast<int>(std::min<long long>(64, (per + 31) / 32 * 32));
 }
 
 template <typename T>
