@@ -33,7 +33,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if not (force or _stale()):
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [NVCC] + FLAGS + os.environ.get("KLUJAX_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return OUT
