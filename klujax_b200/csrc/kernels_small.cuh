@@ -28,6 +28,7 @@ struct Sc<double> {
     __device__ static __forceinline__ V ld(const V* p) { return *p; }
     __device__ static __forceinline__ void st(V* p, V v) { *p = v; }
     __device__ static __forceinline__ void fma_acc(V& acc, V a, V b) { acc = fma(a, b, acc); }
+    __device__ static __forceinline__ void fms_acc(V& acc, V a, V b) { acc = fma(-a, b, acc); }  // acc -= a * b
     __device__ static __forceinline__ V sub(V a, V b) { return a - b; }
     __device__ static __forceinline__ V add(V a, V b) { return a + b; }
     __device__ static __forceinline__ V mul(V a, V b) { return a * b; }
@@ -62,6 +63,12 @@ struct Sc<zc> {
         acc.y = fma(a.x, b.y, acc.y);
         acc.x = fma(-a.y, b.y, acc.x);
         acc.y = fma(a.y, b.x, acc.y);
+    }
+    __device__ static __forceinline__ void fms_acc(V& acc, V a, V b) {  // acc -= a * b
+        acc.x = fma(-a.x, b.x, acc.x);
+        acc.y = fma(-a.x, b.y, acc.y);
+        acc.x = fma(a.y, b.y, acc.x);
+        acc.y = fma(-a.y, b.x, acc.y);
     }
     __device__ static __forceinline__ V sub(V a, V b) { return make_double2(a.x - b.x, a.y - b.y); }
     __device__ static __forceinline__ V add(V a, V b) { return make_double2(a.x + b.x, a.y + b.y); }

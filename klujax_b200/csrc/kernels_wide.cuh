@@ -20,6 +20,9 @@
 
 namespace kb {
 
+#ifndef KW_UNCOND
+#define KW_UNCOND 1
+#endif
 constexpr int kWarpsPerSystem = 4;
 constexpr int kLanesPerSystem = 32 * kWarpsPerSystem;
 constexpr int kStepBytes = kLanesPerSystem * 8;           // one step of one system's lanes
@@ -196,23 +199,23 @@ __global__ void __launch_bounds__(32 * (kWarpsPerSystem * 5 + 1), 1)
                     const uint32_t kind = h & 0xFu;
                     if (kind) {
                         V_t* po = reinterpret_cast<V_t*>(Vb + ((h >> (14 + SHR)) & MSK));
-                        const V_t vo = *po;
-                        typename S::Acc acc = S::acc0();
+                        V_t t = *po;
+#if KW_UNCOND
+                        if (P >= 1) {  // lanes without a pair multiply ZERO by ZERO: no lane-dependent branch
+#else
                         if (P >= 1 && w1) {
+#endif
                             const V_t va = *reinterpret_cast<const V_t*>(Vb + ((w1 >> (14 + SHR)) & MSK));
                             const V_t vb = *reinterpret_cast<const V_t*>(Vb + ((w1 >> SHR) & MSK));
-                            S::mac(acc, va, vb, 0);
+                            S::fms_acc(t, va, vb);
                         }
 #pragma unroll 1
                         for (int q = 2; q <= P; ++q) {
                             const uint32_t w = p[q * kLanesPerSystem];
-                            if (w) {
-                                const V_t va = *reinterpret_cast<const V_t*>(Vb + ((w >> (14 + SHR)) & MSK));
-                                const V_t vb = *reinterpret_cast<const V_t*>(Vb + ((w >> SHR) & MSK));
-                                S::mac(acc, va, vb, q);
-                            }
+                            const V_t va = *reinterpret_cast<const V_t*>(Vb + ((w >> (14 + SHR)) & MSK));
+                            const V_t vb = *reinterpret_cast<const V_t*>(Vb + ((w >> SHR) & MSK));
+                            S::fms_acc(t, va, vb);
                         }
-                        V_t t = S::sub(vo, S::fold(acc));
                         if (kind >= WK_MUL) {
                             if (kind == WK_RECIP) {
                                 bad |= S::bad_pivot(t);

@@ -460,7 +460,8 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
     out.zero_slot = lay.n_val + nx;  // then ONE (= 1), then TRASH
     out.n_slots = out.zero_slot + 3;
     if (out.n_slots > 16383) return false;
-    const uint32_t ONE = out.zero_slot + 1;
+    const uint32_t ZERO = out.zero_slot, ONE = out.zero_slot + 1;
+    const uint32_t idle_op = (ZERO << 18) | (ZERO << 4);  // an operand line without a pair: 0 * 0
     size_t chunk_base = 0;
     int used = kChunkWords;  // forces a first chunk
     auto open_chunk = [&]() {
@@ -487,9 +488,11 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
                 const uint32_t d = tk.div >= 0 ? static_cast<uint32_t>(tk.div) : ONE;
                 const uint32_t kind = tk.kind == TK_RECIP ? 4u : tk.kind == TK_MUL_TRACK ? 3u : tk.kind == TK_MUL ? 2u : 1u;
                 base[k] = (static_cast<uint32_t>(tk.out) << 18) | (d << 4) | kind;
-                for (int q = 0; q < tk.plen; ++q)
-                    base[LANES * (1 + q) + k] = (static_cast<uint32_t>(prog.pa[tk.pbeg + q]) << 18) |
-                                                (static_cast<uint32_t>(prog.pb[tk.pbeg + q]) << 4);
+                for (int q = 0; q < P; ++q)
+                    base[LANES * (1 + q) + k] =
+                        q < tk.plen ? (static_cast<uint32_t>(prog.pa[tk.pbeg + q]) << 18) |
+                                          (static_cast<uint32_t>(prog.pb[tk.pbeg + q]) << 4)
+                                    : idle_op;
             }
             const bool level_end = (i + LANES >= order.size());
             out.ctrl.push_back(static_cast<uint32_t>(P) | (level_end ? 16u : 0u));
