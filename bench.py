@@ -361,7 +361,9 @@ def main():
 
     def e2e_step():
         if w.name in ("cfg5", "cfg2"):
-            x = K.solve_with_symbol(Ai_h, Aj_h, Ax_h, b_h, sym)       # H2D + kernels + status check
+            # H2D + kernels + D2H of x (pipelined per chunk) + status check
+            K.solve_with_symbol(Ai_h, Aj_h, Ax_h, b_h, sym, out=x_h)
+            return
         elif w.name == "cfg4":
             num2 = K.refactor(Ai_h, Aj_h, Ax_h, numeric, sym)
             x = K.solve_with_numeric(num2, b_h, sym)

@@ -221,7 +221,7 @@ def analyze(Ai: Any, Aj: Any, n_col: int) -> KLUHandleManager:
 
 
 _PIPELINE_MIN_SYSTEMS = 8192   # host-resident batches at least this large are streamed in chunks
-_PIPELINE_CHUNKS = 8
+_PIPELINE_CHUNKS = 16
 _streams: dict = {}
 
 
@@ -231,7 +231,7 @@ def _copy_streams(dev: torch.device):
     return _streams[dev]
 
 
-def _solve_symbol(fn: str, Ai, Aj, Ax, b, symbolic, check: bool):
+def _solve_symbol(fn: str, Ai, Aj, Ax, b, symbolic, check: bool, out=None):
     Ai_t, Aj_t, Ax_t, b_t = _as_tensor(Ai), _as_tensor(Aj), _as_tensor(Ax), _as_tensor(b)
     _check_coo(Ai_t, Aj_t, Ax_t)
     Ax_t, b_t, shape = _canonical(Ax_t, b_t, "b")
@@ -245,12 +245,22 @@ def _solve_symbol(fn: str, Ai, Aj, Ax, b, symbolic, check: bool):
     host_batch = (not Ax_t.is_cuda and not b_t.is_cuda and L >= _PIPELINE_MIN_SYSTEMS
                   and Ax_t.dtype == vdt and b_t.dtype == vdt
                   and Ax_t.is_contiguous() and b_t.is_contiguous())
+    out_v = None
+    if out is not None:
+        # extension of the reference signature: a host (ideally pinned) result buffer; with a
+        # host-resident batch the device->host copy of chunk k overlaps the work on chunk k+1
+        if (not isinstance(out, torch.Tensor) or out.is_cuda or out.dtype != vdt
+                or out.numel() != b_t.numel() or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous CPU tensor with the shape and dtype of the result")
+        out_v = out.view(L, n, r)
     if not host_batch:
         Ax_d, b_d = _values(Ax_t, cx), _values(b_t, cx)
         x = torch.empty_like(b_d)
         st, gr = _new_status(L)
         _cabi.check(f(C.c_uint64(sym), L, n, r, nz, _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d),
                       _ptr(b_d), _ptr(x), _ptr(st), _ptr(gr), _stream()))
+        if out_v is not None:
+            out_v.copy_(x, non_blocking=True)
     else:
         # Host-resident batch: systems are independent, so the batch is streamed in chunks on
         # two streams - the host->device copy of chunk k+1 overlaps the kernels of chunk k.
@@ -273,23 +283,29 @@ def _solve_symbol(fn: str, Ai, Aj, Ax, b, symbolic, check: bool):
                 _cabi.check(f(C.c_uint64(sym), hi - lo, n, r, nz, _ptr(Ai_d), _ptr(Aj_d),
                               _ptr(Ax_d[lo:hi]), _ptr(b_d[lo:hi]), _ptr(x[lo:hi]), _ptr(st[lo:hi]),
                               _ptr(gr[lo:hi]), C.c_void_p(s.cuda_stream)))
+                if out_v is not None:
+                    out_v[lo:hi].copy_(x[lo:hi], non_blocking=True)
         for s in streams:
             cur.wait_stream(s)
         for t in (Ax_d, b_d, x, st, gr, Ai_d, Aj_d):
             t.record_stream(streams[0])
             t.record_stream(streams[1])
     _raise_if_failed(st, "klu_factor", check)
+    if out_v is not None:
+        torch.cuda.current_stream().synchronize()  # the caller may read `out` on return
+        return out.view(shape)
     return x.reshape(shape)
 
 
-def solve_with_symbol(Ai, Aj, Ax, b, symbolic, check: bool = True) -> torch.Tensor:
-    """Factor + solve with a precomputed symbolic analysis (klujax.py:376-393)."""
-    return _solve_symbol("solve_with_symbol", Ai, Aj, Ax, b, symbolic, check)
+def solve_with_symbol(Ai, Aj, Ax, b, symbolic, check: bool = True, out=None) -> torch.Tensor:
+    """Factor + solve with a precomputed symbolic analysis (klujax.py:376-393).  `out`
+    (extension): a CPU result buffer filled with pipelined device->host copies."""
+    return _solve_symbol("solve_with_symbol", Ai, Aj, Ax, b, symbolic, check, out)
 
 
-def tsolve_with_symbol(Ai, Aj, Ax, b, symbolic, check: bool = True) -> torch.Tensor:
+def tsolve_with_symbol(Ai, Aj, Ax, b, symbolic, check: bool = True, out=None) -> torch.Tensor:
     """Factor + transpose solve A^T x = b (plain transpose; klujax.py:416-440)."""
-    return _solve_symbol("tsolve_with_symbol", Ai, Aj, Ax, b, symbolic, check)
+    return _solve_symbol("tsolve_with_symbol", Ai, Aj, Ax, b, symbolic, check, out)
 
 
 def solve(Ai, Aj, Ax, b, check: bool = True) -> torch.Tensor:
