@@ -145,6 +145,18 @@ int klujax_cuda_dot_c128(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_
                          const int32_t* Aj_dev, const double* Ax_dev, const double* x_dev,
                          double* b_dev, void* stream);
 
+/* ---- transpose of dot with respect to the values : klujax.py:1695-1716 (dot_transpose:
+ * dAx[m,e] = sum_k ct[m, Ai[e], k] * x[m, Aj[e], k], pure jnp in the reference; here one
+ * gather kernel, used by the fused value-and-vjp of the Python mirror, "next" row f2) */
+int klujax_cuda_dot_transpose_ax_f64(int n_lhs, int n_col, int n_rhs, int n_nz,
+                                     const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                     const double* ct_dev, const double* x_dev, double* dAx_dev,
+                                     void* stream);
+int klujax_cuda_dot_transpose_ax_c128(int n_lhs, int n_col, int n_rhs, int n_nz,
+                                      const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                      const double* ct_dev, const double* x_dev, double* dAx_dev,
+                                      void* stream);
+
 /* ---- host-only introspection (used by the parity tests; no GPU needed) ---- */
 /* Fixes the pivot sequence from one host-resident system of values given in the
  * COO order of the analyze call (what the first numeric call does internally). */

@@ -8,7 +8,8 @@ calling any operator without it (or without a GPU) raises — no CPU fallback.
 """
 __version__ = "0.1.0"
 
-_API = ("solve", "dot", "coalesce", "analyze", "factor", "refactor", "solve_with_symbol",
+_API = ("solve", "dot", "dot_transpose_ax", "solve_with_symbol_value_and_jvp",
+        "solve_with_symbol_value_and_vjp", "coalesce", "analyze", "factor", "refactor", "solve_with_symbol",
         "tsolve_with_symbol", "solve_with_numeric", "tsolve_with_numeric", "refactor_and_solve",
         "free_symbolic", "free_numeric", "KLUHandleManager", "KlujaxCudaError", "last_status")
 

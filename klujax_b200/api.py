@@ -22,7 +22,8 @@ from . import _cabi
 from ._cabi import KlujaxCudaError
 
 __all__ = [
-    "solve", "dot", "coalesce", "analyze", "factor", "refactor", "solve_with_symbol",
+    "solve", "dot", "dot_transpose_ax", "solve_with_symbol_value_and_jvp",
+    "solve_with_symbol_value_and_vjp", "coalesce", "analyze", "factor", "refactor", "solve_with_symbol",
     "tsolve_with_symbol", "solve_with_numeric", "tsolve_with_numeric", "refactor_and_solve",
     "free_symbolic", "free_numeric", "KLUHandleManager", "KlujaxCudaError", "last_status",
 ]
@@ -341,6 +342,66 @@ def dot(Ai, Aj, Ax, x) -> torch.Tensor:
     _cabi.check(f(L, n, r, Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d), _ptr(x_d), _ptr(out),
                   _stream()))
     return out.reshape(shape)
+
+
+def dot_transpose_ax(Ai, Aj, ct, x) -> torch.Tensor:
+    """dAx[m, e] = sum_k ct[m, Ai[e], k] * x[m, Aj[e], k]: the transpose of `dot` with respect to
+    the values (klujax.py:1712-1714, pure jnp in the reference).  ct and x: (n_lhs, n_col, n_rhs)
+    or lower rank as for `dot`; returns (n_lhs, n_nz)."""
+    Ai_t, Aj_t, ct_t, x_t = _as_tensor(Ai), _as_tensor(Aj), _as_tensor(ct), _as_tensor(x)
+    cx = _is_complex(ct_t, x_t)
+    Ai_d, Aj_d = _indices(Ai_t), _indices(Aj_t)
+    while ct_t.ndim < 3:
+        ct_t = ct_t.unsqueeze(0) if ct_t.ndim == 2 else ct_t.unsqueeze(-1)
+    while x_t.ndim < 3:
+        x_t = x_t.unsqueeze(0) if x_t.ndim == 2 else x_t.unsqueeze(-1)
+    if ct_t.shape != x_t.shape:
+        ct_t, x_t = torch.broadcast_tensors(ct_t, x_t)
+    ct_d, x_d = _values(ct_t, cx), _values(x_t, cx)
+    L, n, r = x_d.shape
+    out = torch.empty((L, Ai_d.numel()), dtype=x_d.dtype, device=x_d.device)
+    f = getattr(_cabi.lib(), f"klujax_cuda_dot_transpose_ax_{_suffix(cx)}")
+    _cabi.check(f(L, n, r, Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d), _ptr(ct_d), _ptr(x_d), _ptr(out),
+                  _stream()))
+    return out
+
+
+def solve_with_symbol_value_and_jvp(Ai, Aj, Ax, b, symbolic, t_Ax=None, t_b=None, check: bool = True):
+    """x and dx of `solve_with_symbol` from ONE factorization ("next" row f2).
+
+    Same formula as the reference's JVP rule (klujax.py:1856-1897: x = A^-1 b,
+    dx = A^-1 (t_b - dot(Ai, Aj, t_Ax, x))), which binds `solve_with_symbol` twice and so
+    factors the same A twice; here A is factored once and both right-hand sides are solved
+    from the device-resident factors."""
+    num = factor(Ai, Aj, Ax, symbolic, check=check)
+    try:
+        x = solve_with_numeric(num, b, symbolic)
+        rhs = None if t_b is None else _as_tensor(t_b).to(x.device)
+        if t_Ax is not None:
+            dAx = dot(Ai, Aj, t_Ax, x)
+            rhs = -dAx if rhs is None else rhs - dAx
+        dx = torch.zeros_like(x) if rhs is None else solve_with_numeric(num, rhs, symbolic)
+    finally:
+        num.close()
+    return x, dx
+
+
+def solve_with_symbol_value_and_vjp(Ai, Aj, Ax, b, symbolic, ct, check: bool = True):
+    """x, b_bar and Ax_bar of `solve_with_symbol` from ONE factorization ("next" row f2).
+
+    b_bar = A^-T ct is the reference's transpose rule for b (klujax.py:1948-1957, plain
+    transpose also for complex); Ax_bar[m, e] = -sum_k b_bar[m, Ai[e], k] x[m, Aj[e], k] is the
+    transpose of the JVP's `dot` term (klujax.py:1886-1890 with dot_transpose :1712-1714).
+    The reference factors A three times for this (primal, JVP, transpose)."""
+    num = factor(Ai, Aj, Ax, symbolic, check=check)
+    try:
+        x = solve_with_numeric(num, b, symbolic)
+        b_bar = tsolve_with_numeric(num, ct, symbolic)
+    finally:
+        num.close()
+    Ax_bar = -dot_transpose_ax(Ai, Aj, b_bar, x)
+    Ax_t = _as_tensor(Ax)
+    return x, b_bar, Ax_bar.reshape(Ax_t.shape) if Ax_bar.numel() == Ax_t.numel() else Ax_bar
 
 
 def factor(Ai, Aj, Ax, symbolic, check: bool = True) -> KLUHandleManager:

@@ -456,6 +456,46 @@ __global__ void spmm_kernel(int L, int n, int r, int nz, const int* __restrict__
     for (int w = 0; w < W; ++w) atomicAdd(dst + w, pv[w]);
 }
 
+// dAx[m][e] = sum_k ct[m][Ai[e]][k] * x[m][Aj[e]][k]: transpose of the product above with
+// respect to the values (/root/reference/klujax.py:1712-1714).  Thread per (system, entry).
+template <typename T>
+__global__ void sddmm_kernel(int L, int n, int r, int nz, const int* __restrict__ Ai,
+                             const int* __restrict__ Aj, const typename Sc<T>::V* __restrict__ ct,
+                             const typename Sc<T>::V* __restrict__ x,
+                             typename Sc<T>::V* __restrict__ dAx) {
+    using S = Sc<T>;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)L * nz) return;
+    const int e = static_cast<int>(tid % nz);
+    const long long m = tid / nz;
+    const int i = Ai[e], j = Aj[e];
+    typename S::V acc = S::zero();
+    if (i >= 0 && i < n && j >= 0 && j < n) {
+        const typename S::V* pc = ct + (m * n + i) * r;
+        const typename S::V* px = x + (m * n + j) * r;
+        for (int k = 0; k < r; ++k) S::fma_acc(acc, pc[k], px[k]);
+    }
+    dAx[tid] = acc;
+}
+
+static int coo_sddmm(int cx, int L, int n, int r, int nz, const int* Ai, const int* Aj,
+                     const double* ct, const double* x, double* dAx, cudaStream_t st, std::string& err) {
+    const long long total = (long long)L * nz;
+    if (total == 0) return 0;
+    const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+    if (cx)
+        sddmm_kernel<zc><<<grid, 256, 0, st>>>(L, n, r, nz, Ai, Aj, reinterpret_cast<const double2*>(ct),
+                                               reinterpret_cast<const double2*>(x),
+                                               reinterpret_cast<double2*>(dAx));
+    else
+        sddmm_kernel<double><<<grid, 256, 0, st>>>(L, n, r, nz, Ai, Aj, ct, x, dAx);
+    if (cudaGetLastError() != cudaSuccess) {
+        err = "dot_transpose: launch failed";
+        return KLU_INVALID;
+    }
+    return 0;
+}
+
 static int coo_spmm(int cx, int L, int n, int r, int nz, const int* Ai, const int* Aj,
                     const double* Ax, const double* x, double* b, cudaStream_t st, std::string& err) {
     const size_t bytes = sizeof(double) * (cx ? 2 : 1) * (size_t)L * n * r;

@@ -982,4 +982,20 @@ int klujax_cuda_dot_c128(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_
     return rc ? fail(rc, err) : 0;
 }
 
+// ---- transpose of dot with respect to the values -------------------------------
+int klujax_cuda_dot_transpose_ax_f64(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai,
+                                     const int32_t* Aj, const double* ct, const double* x,
+                                     double* dAx, void* stream) {
+    std::string err;
+    int rc = coo_sddmm(0, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, ct, x, dAx, static_cast<cudaStream_t>(stream), err);
+    return rc ? fail(rc, err) : 0;
+}
+int klujax_cuda_dot_transpose_ax_c128(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai,
+                                      const int32_t* Aj, const double* ct, const double* x,
+                                      double* dAx, void* stream) {
+    std::string err;
+    int rc = coo_sddmm(1, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, ct, x, dAx, static_cast<cudaStream_t>(stream), err);
+    return rc ? fail(rc, err) : 0;
+}
+
 }  // extern "C"

@@ -491,3 +491,40 @@ def test_host_result_buffer_out(K):
             assert torch.equal(out, K.tsolve_with_symbol(Ai, Aj, Ax.cuda(), b.cuda(), sym).cpu())
             with pytest.raises(ValueError):
                 K.solve_with_symbol(Ai, Aj, Ax, b, sym, out=torch.empty(3, dtype=torch.complex128))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_fused_value_and_jvp_vjp(K, dtype):
+    """One factorization serves the primal, the JVP and the transpose solve ("next" row f2):
+    same numbers as the reference's composition of rules (klujax.py:1856-1897, 1948-1957,
+    1712-1714), checked against dense linear algebra."""
+    import torch
+    L, n, r = 3, 12, 2
+    Ai, Aj, Ax, b = synth.ref_style_case(n, 40, L, r, dtype)
+    rng = np.random.default_rng(11)
+    cplx = np.iscomplexobj(Ax)
+    def rnd(shape):
+        v = rng.standard_normal(shape)
+        return v + 1j * rng.standard_normal(shape) if cplx else v
+    t_Ax, t_b, ct = rnd(Ax.shape), rnd(b.shape), rnd(b.shape)
+    with K.analyze(Ai, Aj, n) as sym:
+        x, dx = K.solve_with_symbol_value_and_jvp(Ai, Aj, Ax, b, sym, t_Ax=t_Ax, t_b=t_b)
+        x2, b_bar, Ax_bar = K.solve_with_symbol_value_and_vjp(Ai, Aj, Ax, b, sym, ct)
+        # the reference's own composition: two more factorizations
+        dx_ref = K.solve_with_symbol(Ai, Aj, Ax, torch.from_numpy(t_b).cuda() - K.dot(Ai, Aj, t_Ax, x), sym)
+        b_bar_ref = K.tsolve_with_symbol(Ai, Aj, Ax, ct, sym)
+    assert relerr(np_(dx), np_(dx_ref)) < 1e-12 and relerr(np_(b_bar), np_(b_bar_ref)) < 1e-12
+    assert torch.equal(x, x2)
+    for m in range(L):
+        A = dense(Ai, Aj, Ax[m], n)
+        tA = dense(Ai, Aj, t_Ax[m], n)
+        xm = np.linalg.solve(A, b[m])
+        assert relerr(np_(x)[m], xm) < 1e-11
+        assert relerr(np_(dx)[m], np.linalg.solve(A, t_b[m] - tA @ xm)) < 1e-10
+        bb = np.linalg.solve(A.T, ct[m])
+        assert relerr(np_(b_bar)[m], bb) < 1e-10
+        assert relerr(np_(Ax_bar)[m], -(bb[Ai] * xm[Aj]).sum(-1)) < 1e-10
+    # the gather kernel alone, against numpy
+    g = np_(K.dot_transpose_ax(Ai, Aj, ct, b))
+    assert relerr(g, (ct[:, Ai] * b[:, Aj]).sum(-1)) < 1e-13

@@ -12,7 +12,7 @@ from klujax_b200 import synth
 
 def test_library_exports_every_declared_symbol(cabi):
     names = cabi.declared_symbols()
-    assert len(names) == 27
+    assert len(names) == 29
     lib = cabi.lib()
     for nm in names:
         assert hasattr(lib, nm), nm
