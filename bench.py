@@ -294,7 +294,7 @@ def main():
 
         def step():
             _cabi.check(f(symh, L, n, r, nz, P(Ai_d), P(Aj_d), P(Ax_d), P(b_d), P(x_d), P(st_d), P(gr_d), sp))
-        launches_per_step = 2  # coo_map_kernel + small_kernel (plus one 4-byte memset)
+        launches_per_step = 2  # coo_map_kernel + wide_kernel / small_kernel (plus one 4-byte memset)
     elif w.name == "cfg4":
         numeric = K.factor(Ai_d, Aj_d, Ax_d, sym)
         nh = np.ascontiguousarray(numeric.handle)
@@ -410,9 +410,15 @@ def main():
     achieved = bytes_launch / (ms_total / args.steps * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "kernel": "small_kernel (whole step timed: coo_map_kernel + small_kernel; the map is <1% per "
-                          "profiles/)" if w.name in ("cfg5", "cfg2") else "lv_factor/lv_solve (whole step timed)",
+                "kernel": {"cfg5": "wide_kernel<zc> (whole step timed: coo_map_kernel + wide_kernel; the map is "
+                                   "0.1% per profiles/launches_r01.csv)",
+                           "cfg2": "small_kernel<zc> (whole step timed: coo_map_kernel + small_kernel)"}.get(
+                               w.name, "lv_factor/lv_solve (whole step timed)"),
                 "algorithmic_bytes_per_system": w.algorithmic_bytes_per_system(nnz_lu)}
+    if w.name == "cfg5":  # what actually binds (ncu, profiles/README.md): on-chip, not HBM
+        roofline["binding_resource"] = ("shared-memory wavefronts ~54% of peak and issue slots ~49% busy "
+                                        "(ncu --set full, profiles/): shared-memory capacity (5 systems/SM) x "
+                                        "level latency, not HBM")
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         rec = json.load(open(tr)).get(w.name)
