@@ -91,6 +91,53 @@ def _raise_if_failed(status: torch.Tensor, what: str, check: bool) -> None:
         raise KlujaxCudaError(code, f"{what} failed (singular matrix?) at system {first}")
 
 
+GROWTH_LIMIT = 1000.0 * (1.0 + 1e-9)  # 1 / tol of KLU's pivot rule (klu_defaults: tol = 1e-3)
+_RESEED_ROUNDS = 8
+
+
+def _reseed_failed_certificates(fn: str, cx: bool, Ai_t, Aj_t, Ax_d, b_d, x, st, gr, n: int) -> int:
+    """Pivot parity, second line of defence.  The batch runs with the pivot sequence of its
+    first system; `growth = max |L|` certifies per system that KLU's own partial pivoting
+    (diagonal kept iff >= tol * column max, klu_factor as called at klujax.cpp:310/441) would
+    have kept those pivots.  Systems whose certificate fails (growth > 1/tol) are solved again,
+    still on the GPU, with a pivot sequence seeded from one of THEM (a fresh symbolic handle),
+    until every system is certified or _RESEED_ROUNDS is reached.  Returns how many systems
+    were re-solved.  Needs per-system values (a broadcast Ax has one certificate)."""
+    if Ax_d.shape[0] != b_d.shape[0] or Ax_d.shape[0] < 2:
+        return 0
+    # also systems that hit an exactly zero pivot: with its own row exchanges klu_factor may
+    # still succeed on them (if not, seeding from that system reports KLU_SINGULAR like it)
+    sub = torch.nonzero(((gr > GROWTH_LIMIT) & (st == 0)) | (st == 1)).reshape(-1)
+    if sub.numel() == 0:
+        return 0
+    Ai_h = np.ascontiguousarray(Ai_t.detach().cpu().numpy(), dtype=np.int32)
+    Aj_h = np.ascontiguousarray(Aj_t.detach().cpu().numpy(), dtype=np.int32)
+    Ai_d, Aj_d = _indices(Ai_t), _indices(Aj_t)
+    f = getattr(_cabi.lib(), f"klujax_cuda_{fn}_{_suffix(cx)}")
+    redone = 0
+    for _ in range(_RESEED_ROUNDS):
+        if sub.numel() == 0:
+            break
+        Ls = int(sub.numel())
+        Ax_s, b_s = Ax_d[sub].contiguous(), b_d[sub].contiguous()
+        x_s = torch.empty_like(b_s)
+        st_s = torch.empty(Ls, dtype=torch.int32, device=x.device)
+        gr_s = torch.empty(Ls, dtype=torch.float64, device=x.device)
+        h = _cabi.analyze(Ai_h, Aj_h, n)
+        try:
+            _cabi.check(f(C.c_uint64(h), Ls, n, b_d.shape[2], Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d),
+                          _ptr(Ax_s), _ptr(b_s), _ptr(x_s), _ptr(st_s), _ptr(gr_s), _stream()))
+            torch.cuda.current_stream().synchronize()
+        finally:
+            _cabi.free_symbolic(h)
+        x[sub], st[sub], gr[sub] = x_s, st_s, gr_s
+        redone += Ls
+        again = ((gr_s > GROWTH_LIMIT) & (st_s == 0)) | (st_s == 1)
+        again[0] = False  # the seed system carries its own pivot sequence
+        sub = sub[again]
+    return redone
+
+
 def _canonical(Ax: torch.Tensor, x: torch.Tensor, x_name: str):
     """Shape normalisation of klujax.py:1748-1849 (validate_args).  Returns
     Ax[n_lhs, n_nz], x[n_lhs, n_col, n_rhs] and the caller-facing output shape."""
@@ -291,6 +338,9 @@ def _solve_symbol(fn: str, Ai, Aj, Ax, b, symbolic, check: bool, out=None):
         for t in (Ax_d, b_d, x, st, gr, Ai_d, Aj_d):
             t.record_stream(streams[0])
             t.record_stream(streams[1])
+    if check and _reseed_failed_certificates(fn, cx, Ai_t, Aj_t, Ax_d, b_d, x, st, gr, n):
+        if out_v is not None:
+            out_v.copy_(x, non_blocking=True)
     _raise_if_failed(st, "klu_factor", check)
     if out_v is not None:
         torch.cuda.current_stream().synchronize()  # the caller may read `out` on return

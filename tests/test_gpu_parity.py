@@ -528,3 +528,41 @@ def test_fused_value_and_jvp_vjp(K, dtype):
     # the gather kernel alone, against numpy
     g = np_(K.dot_transpose_ax(Ai, Aj, ct, b))
     assert relerr(g, (ct[:, Ai] * b[:, Aj]).sum(-1)) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("regime", ["0", "1"])
+def test_systems_that_need_other_pivots_are_reseeded(K, oracle, regime, monkeypatch):
+    """The batch runs with the pivot sequence of its first system.  A system whose growth
+    certificate fails (KLU's own rule would have exchanged rows: tiny or zero diagonal) is solved
+    again with a pivot sequence of its own, so x matches the reference's per-system klu_factor."""
+    monkeypatch.setenv("KLUJAX_CUDA_FORCE_REGIME", regime)
+    n, L = 8, 6
+    rng = np.random.default_rng(21)
+    A = rng.standard_normal((n, n)) * (rng.random((n, n)) < 0.5)
+    A += np.diag(4.0 + np.abs(A).sum(1))
+    Ai, Aj = np.nonzero(A)
+    Ai, Aj = Ai.astype(np.int32), Aj.astype(np.int32)
+    Ax = np.tile(A[Ai, Aj], (L, 1)) * (1.0 + 0.05 * rng.standard_normal((L, Ai.size)))
+    dpos = {int(i): k for k, (i, j) in enumerate(zip(Ai, Aj)) if i == j}
+    Ax[2, dpos[3]] = 1e-9     # tiny diagonal: the static pivot would give |L| ~ 1e9
+    Ax[4, dpos[1]] = 0.0      # zero diagonal: the static pivot is exactly singular
+    Ax[4, dpos[5]] = 1e-12
+    b = rng.standard_normal((L, n, 2))
+    so = oracle.analyze(Ai, Aj, n)
+    ref = oracle.solve_with_symbol(Ai, Aj, Ax, b, so)
+    oracle.free_symbolic(so)
+    with K.analyze(Ai, Aj, n) as sym:
+        raw = np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym, check=False))
+        st, gr = (np_(t).copy() for t in K.last_status())
+        assert st.tolist() == [0, 0, 0, 0, 1, 0] and gr[2] > 1e6
+        x = np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym))          # check=True: re-seeds 2 and 4
+        st2, gr2 = (np_(t) for t in K.last_status())
+        assert st2.tolist() == [0] * L and gr2.max() <= 1000.0 * (1 + 1e-9)
+        assert relerr(x, ref) < X_TOL
+        for m in (0, 1, 3, 5):
+            assert np.array_equal(x[m], raw[m])                   # certified systems are untouched
+        xt = np_(K.tsolve_with_symbol(Ai, Aj, Ax, b, sym))
+        for m in range(L):
+            Am = dense(Ai, Aj, Ax[m], n)
+            assert relerr(xt[m], np.linalg.solve(Am.T, b[m])) < 1e-9
