@@ -374,6 +374,8 @@ def solve(Ai, Aj, Ax, b, check: bool = True) -> torch.Tensor:
     f = getattr(_cabi.lib(), f"klujax_cuda_solve_{_suffix(cx)}")
     _cabi.check(f(L, n, r, int(Ai_h.size), _cabi.i32p(Ai_h), _cabi.i32p(Aj_h), _ptr(Ax_d), _ptr(b_d),
                   _ptr(x), _ptr(st), _ptr(gr), _stream()))
+    if check:
+        _reseed_failed_certificates("solve_with_symbol", cx, Ai_t, Aj_t, Ax_d, b_d, x, st, gr, n)
     _raise_if_failed(st, "klu_factor", check)
     return x.reshape(shape)
 
