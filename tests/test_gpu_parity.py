@@ -566,3 +566,53 @@ def test_systems_that_need_other_pivots_are_reseeded(K, oracle, regime, monkeypa
         for m in range(L):
             Am = dense(Ai, Aj, Ax[m], n)
             assert relerr(xt[m], np.linalg.solve(Am.T, b[m])) < 1e-9
+
+
+@pytest.mark.gpu
+def test_cfg4_full_size_properties(K):
+    """BASELINE.json config 4 at full size (n = 20 000, 128 systems, planted BTF): refactor +
+    solve + transpose solve, checked through size-independent properties (residuals of every
+    system through the COO product, status, growth certificate, solve/tsolve adjointness)."""
+    import torch
+    pat = synth.MnaPattern(n=20000)
+    n, L = pat.n, 128
+    Ai, Aj = torch.from_numpy(pat.Ai).cuda(), torch.from_numpy(pat.Aj).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    b = torch.randn(L, n, 1, dtype=torch.float64, device="cuda", generator=g)
+    c = torch.randn(L, n, 1, dtype=torch.float64, device="cuda", generator=g)
+    with K.analyze(pat.Ai, pat.Aj, n) as sym, K.factor(Ai, Aj, torch.from_numpy(pat.values(0, L)).cuda(), sym) as num:
+        Ax = torch.from_numpy(pat.values(3, L)).cuda()
+        num2 = K.refactor(Ai, Aj, Ax, num, sym)
+        st, gr = K.last_status()
+        assert int(st.abs().max()) == 0 and float(gr.max()) <= 1000.0
+        x = K.solve_with_numeric(num2, b, sym)
+        y = K.tsolve_with_numeric(num2, c, sym)
+    bn = torch.linalg.vector_norm(b, dim=1)
+    assert float((torch.linalg.vector_norm(K.dot(Ai, Aj, Ax, x) - b, dim=1) / bn).max()) < RES_TOL
+    At_y = K.dot(Aj, Ai, Ax, y)  # transposed triplets
+    assert float((torch.linalg.vector_norm(At_y - c, dim=1) / torch.linalg.vector_norm(c, dim=1)).max()) < RES_TOL
+    # <A^-T c, b> == <c, A^-1 b>
+    lhs, rhs = (y * b).sum((1, 2)), (c * x).sum((1, 2))
+    assert float(((lhs - rhs).abs() / (lhs.abs() + rhs.abs() + 1e-300)).max()) < 1e-9
+
+
+@pytest.mark.gpu
+def test_cfg3_full_grid_properties(K):
+    """BASELINE.json config 3's matrix at full size (256 x 256 Poisson, n = 65 536), with a
+    reduced batch (4 systems x 8 right-hand sides) so that the test stays short: factor once,
+    solve_with_numeric, residual of every right-hand side and linearity."""
+    import torch
+    g, L, r = 256, 4, 8
+    Ai_h, Aj_h, Ax_h = synth.poisson2d(g, L)
+    n = g * g
+    Ai, Aj, Ax = torch.from_numpy(Ai_h).cuda(), torch.from_numpy(Aj_h).cuda(), torch.from_numpy(Ax_h).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    b = torch.randn(L, n, r, dtype=torch.float64, device="cuda", generator=gen)
+    with K.analyze(Ai_h, Aj_h, n) as sym, K.factor(Ai, Aj, Ax, sym) as num:
+        st, gr = K.last_status()
+        assert int(st.abs().max()) == 0 and float(gr.max()) <= 1000.0
+        x = K.solve_with_numeric(num, b, sym)
+        x2 = K.solve_with_numeric(num, b[:, :, :1] - 2.0 * b[:, :, 1:2], sym)
+    res = torch.linalg.vector_norm(K.dot(Ai, Aj, Ax, x) - b, dim=1) / torch.linalg.vector_norm(b, dim=1)
+    assert float(res.max()) < RES_TOL
+    assert float((x2 - (x[:, :, :1] - 2.0 * x[:, :, 1:2])).abs().max() / x.abs().max()) < 1e-12
