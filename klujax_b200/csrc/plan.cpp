@@ -453,9 +453,70 @@ namespace kb {
 // a step is one header line (per lane: out<<18 | pivot-or-ONE<<4 | kind) and P operand lines
 // (per lane: a<<18 | b<<4, 0 = nothing), P = longest task of the step (tasks are sorted by
 // length).  ctrl[step] = P | level-ends<<4; steps never straddle a chunk.
-bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out) {
+namespace {
+
+// Lane order of the tasks of one level for the multi-warp kernel.  A 16-byte (8-byte)
+// shared-memory access of a warp is served in groups of 8 (16) consecutive lanes; a group costs
+// one wavefront per DISTINCT address that shares a 16-byte (8-byte) bank column with another
+// one.  Tasks of a level are independent, so they are dealt greedily into lane groups such that
+// inside a group the destinations, the first operands and the second operands each fall into
+// different bank columns (equal addresses are a broadcast and cost nothing).
+void order_for_banks(const TaskProgram& prog, std::vector<int>& order, int group) {
+    const size_t n = order.size();
+    if (n <= 1) return;
+    auto slot_of = [&](int t, int cls) -> int {
+        const Task& tk = prog.tasks[t];
+        if (cls == 0) return tk.out;
+        if (tk.plen == 0) return -1;
+        return cls == 1 ? prog.pa[tk.pbeg] : prog.pb[tk.pbeg];
+    };
+    std::vector<char> used(n, 0);
+    std::vector<int> result;
+    result.reserve(n);
+    std::vector<int> members;
+    size_t first_free = 0;
+    while (result.size() < n) {
+        while (used[first_free]) ++first_free;
+        members.clear();
+        members.push_back(static_cast<int>(first_free));
+        used[first_free] = 1;
+        while (static_cast<int>(members.size()) < group && result.size() + members.size() < n) {
+            int best = -1, best_cost = 1 << 30;
+            for (size_t c = first_free + 1; c < n && best_cost > 0; ++c) {
+                if (used[c]) continue;
+                int cost = 0;
+                for (int cls = 0; cls < 3; ++cls) {
+                    const int sc = slot_of(order[c], cls);
+                    if (sc < 0) continue;
+                    bool same = false, clash = false;
+                    for (int m : members) {
+                        const int sm = slot_of(order[m], cls);
+                        if (sm < 0) continue;
+                        if (sm == sc) same = true;
+                        else if ((sm % group) == (sc % group)) clash = true;
+                    }
+                    if (!same && clash) ++cost;
+                }
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best = static_cast<int>(c);
+                }
+            }
+            if (best < 0) break;
+            used[best] = 1;
+            members.push_back(best);
+        }
+        for (int m : members) result.push_back(order[m]);
+    }
+    order.swap(result);
+}
+
+}  // namespace
+
+bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out, int elem_bytes) {
     out = PackedProgram();
     constexpr int LANES = 128;
+    const bool bank_order = !(std::getenv("KLUJAX_CUDA_BANK_ORDER") && std::atoi(std::getenv("KLUJAX_CUDA_BANK_ORDER")) == 0);
     const int nx = (prog.mode == PM_FACTOR) ? 0 : lay.n * prog.rc;
     out.zero_slot = lay.n_val + nx;  // then ONE (= 1), then TRASH
     out.n_slots = out.zero_slot + 3;
@@ -476,9 +537,11 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
         const int tb = prog.level_ptr[l], te = prog.level_ptr[l + 1];
         order.resize(te - tb);
         for (int t = tb; t < te; ++t) order[t - tb] = t;  // already sorted by length, longest first
+        if (bank_order) order_for_banks(prog, order, 128 / elem_bytes);
         for (size_t i = 0; i < order.size(); i += LANES) {
             const size_t cnt = std::min<size_t>(LANES, order.size() - i);
-            const int P = prog.tasks[order[i]].plen;
+            int P = 0;
+            for (size_t k = 0; k < cnt; ++k) P = std::max(P, prog.tasks[order[i + k]].plen);
             if (P > 7) return false;
             const int words = LANES * (1 + P);
             if (used + words > kChunkWords) open_chunk();
