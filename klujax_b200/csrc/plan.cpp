@@ -208,6 +208,78 @@ struct Leveler {
 
 }  // namespace
 
+namespace {
+
+// Step balancing for the multi-warp kernel.  A level of c tasks costs ceil(c / lanes) steps
+// whatever the fill of its last step.  A partial update of the refactorization
+// (V[out] -= V[a]*V[b] with a, b finished entries of L and U, which never change again) may run
+// at any later level before the task that finishes its destination, as long as no other task
+// of that destination sits there.  So the tasks in a level's last, partly filled step are
+// deferred into the free lanes of a later level's last step whenever that removes a step.
+void rebalance_levels(TaskProgram& prog, int n_val, int lanes) {
+    const int nl = prog.nlevels;
+    if (nl < 2) return;
+    std::vector<int> final_level(n_val, 0);
+    std::vector<std::vector<int>> by_level(nl + 1);
+    for (size_t t = 0; t < prog.tasks.size(); ++t) {
+        const Task& k = prog.tasks[t];
+        by_level[k.level].push_back(static_cast<int>(t));
+        if (k.out < n_val) final_level[k.out] = std::max(final_level[k.out], k.level);
+    }
+    // (destination, level) pairs in use: one writer per destination and level
+    std::vector<std::vector<int>> dest_levels(n_val);
+    for (const Task& k : prog.tasks)
+        if (k.out < n_val) dest_levels[k.out].push_back(k.level);
+    auto busy = [&](int out, int lvl) {
+        for (int l : dest_levels[out])
+            if (l == lvl) return true;
+        return false;
+    };
+    auto movable = [&](const Task& k) {
+        if (k.kind != TK_SUB || k.out >= n_val || k.plen == 0) return false;
+        for (int q = 0; q < k.plen; ++q)
+            if (prog.pa[k.pbeg + q] >= n_val || prog.pb[k.pbeg + q] >= n_val) return false;
+        return k.level < final_level[k.out];
+    };
+    const int horizon = 6;
+    for (int l = 1; l <= nl; ++l) {
+        const int c = static_cast<int>(by_level[l].size());
+        const int rem = c % lanes;
+        if (rem == 0 || c < lanes) continue;  // only trim a partly filled EXTRA step
+        for (int l2 = l + 1; l2 <= std::min(nl, l + horizon); ++l2) {
+            const int c2 = static_cast<int>(by_level[l2].size());
+            const int used2 = c2 % lanes;
+            if (used2 == 0 || used2 + rem > lanes) continue;  // no free lanes in a last step there
+            // collect rem movable tasks of level l that may run at l2
+            std::vector<int> pick;
+            for (int idx = c - 1; idx >= 0 && static_cast<int>(pick.size()) < rem; --idx) {
+                const Task& k = prog.tasks[by_level[l][idx]];
+                if (movable(k) && l2 < final_level[k.out] && !busy(k.out, l2)) pick.push_back(idx);
+            }
+            if (static_cast<int>(pick.size()) < rem) continue;
+            for (int idx : pick) {  // descending indices: erase is safe
+                const int t = by_level[l][idx];
+                Task& k = prog.tasks[t];
+                for (int& dl : dest_levels[k.out])
+                    if (dl == l) dl = l2;
+                k.level = l2;
+                by_level[l2].push_back(t);
+                by_level[l].erase(by_level[l].begin() + idx);
+            }
+            break;
+        }
+    }
+    std::stable_sort(prog.tasks.begin(), prog.tasks.end(), [](const Task& a, const Task& b) {
+        if (a.level != b.level) return a.level < b.level;
+        return a.plen > b.plen;
+    });
+    prog.level_ptr.assign(nl + 1, 0);
+    for (const Task& t : prog.tasks) prog.level_ptr[t.level]++;
+    for (int l = 0; l < nl; ++l) prog.level_ptr[l + 1] += prog.level_ptr[l];
+}
+
+}  // namespace
+
 void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
                    int rc, TaskProgram& prog, int split) {
     const int n = lay.n;
@@ -348,6 +420,9 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
     prog.level_ptr.assign(maxlvl + 1, 0);
     for (const Task& t : prog.tasks) prog.level_ptr[t.level]++;
     for (int l = 0; l < maxlvl; ++l) prog.level_ptr[l + 1] += prog.level_ptr[l];
+    if (split >= 100 && do_factor &&
+        !(std::getenv("KLUJAX_CUDA_REBALANCE") && std::atoi(std::getenv("KLUJAX_CUDA_REBALANCE")) == 0))
+        rebalance_levels(prog, lay.n_val, 128);
 }
 
 bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out) {
