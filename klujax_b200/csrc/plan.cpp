@@ -241,33 +241,51 @@ void rebalance_levels(TaskProgram& prog, int n_val, int lanes) {
             if (prog.pa[k.pbeg + q] >= n_val || prog.pb[k.pbeg + q] >= n_val) return false;
         return k.level < final_level[k.out];
     };
-    const int horizon = 6;
-    for (int l = 1; l <= nl; ++l) {
-        const int c = static_cast<int>(by_level[l].size());
-        const int rem = c % lanes;
-        if (rem == 0 || c < lanes) continue;  // only trim a partly filled EXTRA step
-        for (int l2 = l + 1; l2 <= std::min(nl, l + horizon); ++l2) {
-            const int c2 = static_cast<int>(by_level[l2].size());
-            const int used2 = c2 % lanes;
-            if (used2 == 0 || used2 + rem > lanes) continue;  // no free lanes in a last step there
-            // collect rem movable tasks of level l that may run at l2
-            std::vector<int> pick;
-            for (int idx = c - 1; idx >= 0 && static_cast<int>(pick.size()) < rem; --idx) {
+    const int horizon = 16;
+    // moves exactly m tasks out of level l into free lanes of the last steps of later levels
+    // (possibly several of them); all or nothing
+    auto try_shrink = [&](int l, int m) {
+        std::vector<std::pair<int, int>> plan;  // (index in by_level[l], target level)
+        std::vector<char> taken(by_level[l].size(), 0);
+        int placed = 0;
+        for (int l2 = l + 1; l2 <= std::min(nl, l + horizon) && placed < m; ++l2) {
+            const int used2 = static_cast<int>(by_level[l2].size()) % lanes;
+            if (used2 == 0) continue;
+            int room = lanes - used2;
+            for (int idx = static_cast<int>(by_level[l].size()) - 1; idx >= 0 && room > 0 && placed < m; --idx) {
+                if (taken[idx]) continue;
                 const Task& k = prog.tasks[by_level[l][idx]];
-                if (movable(k) && l2 < final_level[k.out] && !busy(k.out, l2)) pick.push_back(idx);
+                if (!movable(k) || l2 >= final_level[k.out] || busy(k.out, l2)) continue;
+                taken[idx] = 1;
+                plan.emplace_back(idx, l2);
+                --room;
+                ++placed;
             }
-            if (static_cast<int>(pick.size()) < rem) continue;
-            for (int idx : pick) {  // descending indices: erase is safe
-                const int t = by_level[l][idx];
-                Task& k = prog.tasks[t];
-                for (int& dl : dest_levels[k.out])
-                    if (dl == l) dl = l2;
-                k.level = l2;
-                by_level[l2].push_back(t);
-                by_level[l].erase(by_level[l].begin() + idx);
-            }
-            break;
         }
+        if (placed < m) return false;
+        std::sort(plan.begin(), plan.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first > y.first; });
+        for (const auto& mv : plan) {  // descending indices: erase is safe
+            const int t = by_level[l][mv.first];
+            Task& k = prog.tasks[t];
+            for (int& dl : dest_levels[k.out])
+                if (dl == l) dl = mv.second;
+            k.level = mv.second;
+            by_level[mv.second].push_back(t);
+            by_level[l].erase(by_level[l].begin() + mv.first);
+        }
+        return true;
+    };
+    for (int l = 1; l <= nl; ++l) {  // trim partly filled EXTRA steps
+        const int c = static_cast<int>(by_level[l].size());
+        if (c >= lanes && c % lanes) try_shrink(l, c % lanes);
+    }
+    for (int pass = 0; pass < 4; ++pass) {  // then whole steps, while free lanes remain downstream
+        bool any = false;
+        for (int l = 1; l <= nl; ++l) {
+            const int c = static_cast<int>(by_level[l].size());
+            if (c >= 2 * lanes && c % lanes == 0) any |= try_shrink(l, lanes);
+        }
+        if (!any) break;
     }
     std::stable_sort(prog.tasks.begin(), prog.tasks.end(), [](const Task& a, const Task& b) {
         if (a.level != b.level) return a.level < b.level;
