@@ -574,9 +574,10 @@ void order_for_banks(const TaskProgram& prog, std::vector<int>& order, int group
         members.push_back(static_cast<int>(first_free));
         used[first_free] = 1;
         while (static_cast<int>(members.size()) < group && result.size() + members.size() < n) {
-            int best = -1, best_cost = 1 << 30;
-            for (size_t c = first_free + 1; c < n && best_cost > 0; ++c) {
+            int best = -1, best_cost = 1 << 30, seen = 0;
+            for (size_t c = first_free + 1; c < n && best_cost > 0 && seen < 512; ++c) {  // bounded scan
                 if (used[c]) continue;
+                ++seen;
                 int cost = 0;
                 for (int cls = 0; cls < 3; ++cls) {
                     const int sc = slot_of(order[c], cls);
