@@ -83,9 +83,10 @@ struct LevelCall {
     const int *pnum = nullptr, *q = nullptr, *sysidx = nullptr;
     int32_t* status = nullptr;
     double* growth = nullptr;
-    void* V = nullptr;   // [n_val][lpad]
-    double* Rs = nullptr;  // [n][lpad]
+    void* V = nullptr;   // [n_val][lpad] batch-interleaved, or [L][n_val] system-major
+    double* Rs = nullptr;  // [n][lpad], or [L][n]
     long long lpad = 0;
+    int sysmajor = 0;    // layout of V / Rs (see level_run_t)
     cudaStream_t st = nullptr;
 };
 
@@ -94,7 +95,7 @@ template <typename T>
 __global__ void lv_scatter(int L, int nz, const typename Sc<T>::V* __restrict__ Ax,
                            long long ax_stride, const int* __restrict__ coo_dst,
                            const int* __restrict__ sysidx, typename Sc<T>::V* __restrict__ V,
-                           long long lpad) {
+                           long long lpad, long long ss) {
     // 32 x 32 tile through shared memory: read along e, write along the system axis
     __shared__ typename Sc<T>::V tile[32][33];
     const int e0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
@@ -108,20 +109,20 @@ __global__ void lv_scatter(int L, int nz, const typename Sc<T>::V* __restrict__ 
         if (e < nz && m < L) {
             const int d = __ldg(coo_dst + e);
             const int sm = sysidx ? sysidx[m] : m;
-            if (d >= 0) V[(long long)d * lpad + sm] = tile[threadIdx.x][de];
+            if (d >= 0) V[(long long)d * lpad + (long long)sm * ss] = tile[threadIdx.x][de];
         }
     }
 }
 
 template <typename T>
 __global__ void lv_zero_slots(int L, int n_val, const int* __restrict__ sysidx,
-                              typename Sc<T>::V* __restrict__ V, long long lpad) {
+                              typename Sc<T>::V* __restrict__ V, long long lpad, long long ss) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)n_val * L;
     for (long long i = tid; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int m = static_cast<int>(i % L);
         const long long s = i / L;
-        V[s * lpad + (sysidx ? sysidx[m] : m)] = Sc<T>::zero();
+        V[s * lpad + (long long)(sysidx ? sysidx[m] : m) * ss] = Sc<T>::zero();
     }
 }
 
@@ -130,7 +131,7 @@ template <typename T>
 __global__ void lv_rowscale(int L, int n, const int* __restrict__ rs_ptr,
                             const int* __restrict__ rs_slot, const int* __restrict__ sysidx,
                             typename Sc<T>::V* __restrict__ V, double* __restrict__ Rs,
-                            long long lpad) {
+                            long long lpad, long long ss, long long rlp, long long rss) {
     using S = Sc<T>;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (long long)n * L) return;
@@ -138,11 +139,11 @@ __global__ void lv_rowscale(int L, int n, const int* __restrict__ rs_ptr,
     const int sm = sysidx ? sysidx[m] : m;
     const int pb = rs_ptr[i], pe = rs_ptr[i + 1];
     double mx = 0.0;
-    for (int p = pb; p < pe; ++p) mx = fmax(mx, S::mag(V[(long long)rs_slot[p] * lpad + sm]));
+    for (int p = pb; p < pe; ++p) mx = fmax(mx, S::mag(V[(long long)rs_slot[p] * lpad + (long long)sm * ss]));
     if (mx == 0.0) mx = 1.0;
-    Rs[(long long)i * lpad + sm] = mx;
+    Rs[(long long)i * rlp + (long long)sm * rss] = mx;
     for (int p = pb; p < pe; ++p) {
-        typename S::V* q = V + (long long)rs_slot[p] * lpad + sm;
+        typename S::V* q = V + (long long)rs_slot[p] * lpad + (long long)sm * ss;
         *q = S::rdiv(*q, mx);
     }
 }
@@ -153,6 +154,8 @@ struct LvArgs {
     const int* level_ptr;
     int nlevels, n_val, r, slice;   // slice: batch columns owned by one CTA
     long long L, lpad, Q;           // Q = L * r right-hand-side columns in the solve
+    long long vss;                  // V[slot * lpad + system * vss]
+    long long xrs, xcs;             // X[row * xrs + column * xcs]
     void* V;
     void* X;
     const int* sysidx;
@@ -194,21 +197,21 @@ __global__ void __launch_bounds__(1024) lv_factor(const LvArgs a) {
             for (int it = threadIdx.x; it < items; it += blockDim.x) {
                 const int tq = it / ncol;
                 const int t = tb + tq, m = static_cast<int>(s0) + (it - tq * ncol);
-                const int sm = a.sysidx ? a.sysidx[m] : m;
+                const long long sm = a.sysidx ? a.sysidx[m] : m;
                 const bool pre = it == static_cast<int>(threadIdx.x);
                 const int4 rec = pre ? cur_rec : __ldg(a.task + 2 * t);
                 const int4 first = pre ? cur_first : __ldg(a.task + 2 * t + 1);
                 const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
                 const int2* pr = a.pair + rec.z;
-                V_t* o = V + (long long)rec.x * a.lpad + sm;
+                V_t* o = V + (long long)rec.x * a.lpad + sm * a.vss;
                 const V_t o0 = *o;
                 V_t acc = S::zero();
-                if (plen) S::fma_acc(acc, V[(long long)first.x * a.lpad + sm], V[(long long)first.y * a.lpad + sm]);
+                if (plen) S::fma_acc(acc, V[(long long)first.x * a.lpad + sm * a.vss], V[(long long)first.y * a.lpad + sm * a.vss]);
 #pragma unroll 4
                 for (int p = 0; p < plen - 1; ++p) {
                     const int2 ab = __ldg(pr + p);
-                    const V_t x = V[(long long)ab.x * a.lpad + sm];
-                    const V_t y = V[(long long)ab.y * a.lpad + sm];
+                    const V_t x = V[(long long)ab.x * a.lpad + sm * a.vss];
+                    const V_t y = V[(long long)ab.y * a.lpad + sm * a.vss];
                     S::fma_acc(acc, x, y);
                 }
                 V_t v = S::sub(o0, acc);
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(1024) lv_factor(const LvArgs a) {
                     if (S::bad_pivot(v)) a.bad[m] = 1;
                     v = S::recip(v);
                 } else if (kind >= TK_MUL) {
-                    v = S::mul(v, V[(long long)rec.y * a.lpad + sm]);
+                    v = S::mul(v, V[(long long)rec.y * a.lpad + sm * a.vss]);
                     if (kind == TK_MUL_TRACK)
                         atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v)));
                 }
@@ -250,25 +253,25 @@ __global__ void __launch_bounds__(1024) lv_solve(const LvArgs a) {
                 const int t = tb + tq;
                 const long long q = s0 + (it - (long long)tq * ncol);
                 const int m = static_cast<int>(q / a.r);
-                const int sm = a.sysidx ? a.sysidx[m] : m;
+                const long long sm = a.sysidx ? a.sysidx[m] : m;
                 const int4 rec = __ldg(a.task + 2 * t), first = __ldg(a.task + 2 * t + 1);
                 const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
                 const int2* pr = a.pair + rec.z;
-                V_t* o = X + (long long)(rec.x - a.n_val) * a.Q + q;
+                V_t* o = X + (long long)(rec.x - a.n_val) * a.xrs + q * a.xcs;
                 const V_t o0 = *o;
                 V_t acc = S::zero();
                 if (plen)
-                    S::fma_acc(acc, __ldg(V + (long long)first.x * a.lpad + sm),
-                               X[(long long)(first.y - a.n_val) * a.Q + q]);
+                    S::fma_acc(acc, __ldg(V + (long long)first.x * a.lpad + sm * a.vss),
+                               X[(long long)(first.y - a.n_val) * a.xrs + q * a.xcs]);
 #pragma unroll 4
                 for (int p = 0; p < plen - 1; ++p) {
                     const int2 ab = __ldg(pr + p);
-                    const V_t lu = __ldg(V + (long long)ab.x * a.lpad + sm);
-                    const V_t xv = X[(long long)(ab.y - a.n_val) * a.Q + q];
+                    const V_t lu = __ldg(V + (long long)ab.x * a.lpad + sm * a.vss);
+                    const V_t xv = X[(long long)(ab.y - a.n_val) * a.xrs + q * a.xcs];
                     S::fma_acc(acc, lu, xv);
                 }
                 V_t v = S::sub(o0, acc);
-                if (kind >= TK_MUL) v = S::mul(v, __ldg(V + (long long)rec.y * a.lpad + sm));
+                if (kind >= TK_MUL) v = S::mul(v, __ldg(V + (long long)rec.y * a.lpad + sm * a.vss));
                 *o = v;
             }
             __syncthreads();
@@ -280,8 +283,9 @@ __global__ void __launch_bounds__(1024) lv_solve(const LvArgs a) {
 template <typename T>
 __global__ void lv_load_x(int L, int n, int r, const typename Sc<T>::V* __restrict__ b,
                           long long b_stride, const int* __restrict__ perm, int scale,
-                          const double* __restrict__ Rs, long long lpad,
-                          const int* __restrict__ sysidx, typename Sc<T>::V* __restrict__ X) {
+                          const double* __restrict__ Rs, long long rlp, long long rss,
+                          const int* __restrict__ sysidx, typename Sc<T>::V* __restrict__ X,
+                          long long xrs, long long xcs) {
     using S = Sc<T>;
     const long long Q = (long long)L * r;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -291,15 +295,15 @@ __global__ void lv_load_x(int L, int n, int r, const typename Sc<T>::V* __restri
     const int m = static_cast<int>(q / r), c = static_cast<int>(q % r);
     const int src = perm[k];
     typename S::V v = b[(long long)m * b_stride + (long long)src * r + c];
-    if (scale) v = S::rdiv(v, Rs[(long long)src * lpad + (sysidx ? sysidx[m] : m)]);
-    X[(long long)k * Q + q] = v;
+    if (scale) v = S::rdiv(v, Rs[(long long)src * rlp + (long long)(sysidx ? sysidx[m] : m) * rss]);
+    X[(long long)k * xrs + q * xcs] = v;
 }
 
 template <typename T>
 __global__ void lv_store_x(int L, int n, int r, typename Sc<T>::V* __restrict__ x,
                            const int* __restrict__ perm, int scale, const double* __restrict__ Rs,
-                           long long lpad, const int* __restrict__ sysidx,
-                           const typename Sc<T>::V* __restrict__ X) {
+                           long long rlp, long long rss, const int* __restrict__ sysidx,
+                           const typename Sc<T>::V* __restrict__ X, long long xrs, long long xcs) {
     using S = Sc<T>;
     const long long Q = (long long)L * r;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,8 +312,8 @@ __global__ void lv_store_x(int L, int n, int r, typename Sc<T>::V* __restrict__ 
     const int k = static_cast<int>(tid / Q);
     const int m = static_cast<int>(q / r), c = static_cast<int>(q % r);
     const int dst = perm[k];
-    typename S::V v = X[(long long)k * Q + q];
-    if (scale) v = S::rdiv(v, Rs[(long long)dst * lpad + (sysidx ? sysidx[m] : m)]);
+    typename S::V v = X[(long long)k * xrs + q * xcs];
+    if (scale) v = S::rdiv(v, Rs[(long long)dst * rlp + (long long)(sysidx ? sysidx[m] : m) * rss]);
     x[((long long)m * n + dst) * r + c] = v;
 }
 
@@ -337,6 +341,20 @@ static int pick_slice(long long ncols, int num_sms) {
     return static_cast<int>(std::min<long long>(64, (per + 31) / 32 * 32));
 }
 
+// System-major V (one system per CTA) when the batch is not larger than the machine.
+static int want_sysmajor(long long L, int num_sms) {
+    if (const char* e = std::getenv("KLUJAX_CUDA_SYSMAJOR")) return std::atoi(e) != 0;
+    return L <= num_sms;
+}
+
+// Threads per CTA of the level kernels: enough for the widest level of the slice, at most 1024.
+static int level_threads(int max_level_tasks, int slice) {
+    if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_THREADS")) return std::max(32, std::min(1024, std::atoi(e)));
+    (void)max_level_tasks;
+    (void)slice;
+    return 1024;
+}
+
 template <typename T>
 static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::string& err) {
     using V_t = typename Sc<T>::V;
@@ -351,6 +369,11 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
     V_t* V = static_cast<V_t*>(c.V);
     double* Rs = c.Rs;
     long long lpad = c.lpad;
+    // Layout of V / Rs.  Batch-interleaved (V[slot][system]) makes the accesses of consecutive
+    // threads = consecutive systems coalesced; with at most one system per SM a CTA owns ONE
+    // system and its threads walk different slots of it, so the system-major layout
+    // (V[system][slot]) keeps a CTA's working set in contiguous lines of its own L1/L2 sectors.
+    int sysmajor = c.sysmajor;
     void *tmpV = nullptr, *tmpRs = nullptr, *tmpX = nullptr, *tmpAux = nullptr;
     auto cleanup = [&]() {
         // stream-ordered frees: the buffers stay valid for the work enqueued above
@@ -361,6 +384,7 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
     };
     if (own_storage) {
         lpad = (c.L + 31) / 32 * 32;
+        sysmajor = want_sysmajor(c.L, c.num_sms);
         if (!chk(cudaMallocAsync(&tmpV, sizeof(V_t) * (size_t)c.n_val * lpad, c.st), "alloc V") ||
             !chk(cudaMallocAsync(&tmpRs, sizeof(double) * (size_t)c.n * lpad, c.st), "alloc Rs")) {
             cleanup();
@@ -379,24 +403,26 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
     unsigned long long* growth2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(tmpAux) + 64);
     int* bad = reinterpret_cast<int*>(growth2 + c.L);
 
+    const long long v_slot = sysmajor ? 1 : lpad, v_sys = sysmajor ? c.n_val : 1;
+    const long long r_row = sysmajor ? 1 : lpad, r_sys = sysmajor ? c.n : 1;
     const bool factor = (pf != nullptr);
     if (factor) {
         const long long tot = (long long)c.n_val * c.L;
         const int zb = static_cast<int>(std::min<long long>((tot + 255) / 256, 148LL * 16));
-        lv_zero_slots<T><<<zb, 256, 0, c.st>>>(c.L, c.n_val, c.sysidx, V, lpad);
+        lv_zero_slots<T><<<zb, 256, 0, c.st>>>(c.L, c.n_val, c.sysidx, V, v_slot, v_sys);
         dim3 tb(32, 8), tg((c.nz + 31) / 32, (c.L + 31) / 32);
         lv_scatter<T><<<tg, tb, 0, c.st>>>(c.L, c.nz, static_cast<const V_t*>(c.Ax), c.ax_stride,
-                                          c.coo_dst, c.sysidx, V, lpad);
+                                          c.coo_dst, c.sysidx, V, v_slot, v_sys);
         const long long rt = (long long)c.n * c.L;
         lv_rowscale<T><<<static_cast<unsigned>((rt + 255) / 256), 256, 0, c.st>>>(
-            c.L, c.n, c.rs_ptr, c.rs_slot, c.sysidx, V, Rs, lpad);
+            c.L, c.n, c.rs_ptr, c.rs_slot, c.sysidx, V, Rs, v_slot, v_sys, r_row, r_sys);
         LvArgs a;
         a.task = pf->d_task; a.pair = pf->d_pair; a.level_ptr = pf->d_level_ptr;
-        a.nlevels = pf->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = 1; a.lpad = lpad; a.Q = c.L;
+        a.nlevels = pf->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = 1; a.lpad = v_slot; a.vss = v_sys; a.xrs = 0; a.xcs = 0; a.Q = c.L;
         a.V = V; a.X = nullptr; a.sysidx = c.sysidx; a.bad = bad; a.growth2 = growth2;
         a.slice = pick_slice(c.L, c.num_sms);
         const int grid = static_cast<int>(std::min<long long>((c.L + a.slice - 1) / a.slice, 2LL * c.num_sms));
-        lv_factor<T><<<grid, 1024, 0, c.st>>>(a);
+        lv_factor<T><<<grid, level_threads(pf->max_level_tasks, a.slice), 0, c.st>>>(a);
         lv_finish_status<<<(c.L + 255) / 256, 256, 0, c.st>>>(c.L, bad, growth2, c.pattern_bad,
                                                             c.status, c.growth);
     }
@@ -409,18 +435,22 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
         }
         V_t* X = static_cast<V_t*>(tmpX);
         const long long tot = Q * c.n;
+        // X: columns interleaved (X[row][column]) for wide slices, column-major for one column per CTA
+        const int xslice = pick_slice(Q, c.num_sms);
+        const long long x_row = xslice == 1 ? 1 : Q, x_col = xslice == 1 ? c.n : 1;
         lv_load_x<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
             c.L, c.n, c.r, static_cast<const V_t*>(c.b), c.b_stride, tr ? c.q : c.pnum, tr ? 0 : 1,
-            Rs, lpad, c.sysidx, X);
+            Rs, r_row, r_sys, c.sysidx, X, x_row, x_col);
         LvArgs a;
         a.task = ps->d_task; a.pair = ps->d_pair; a.level_ptr = ps->d_level_ptr;
-        a.nlevels = ps->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = c.r; a.lpad = lpad; a.Q = Q;
+        a.nlevels = ps->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = c.r; a.lpad = v_slot; a.vss = v_sys; a.xrs = x_row; a.xcs = x_col; a.Q = Q;
         a.V = V; a.X = X; a.sysidx = c.sysidx; a.bad = bad; a.growth2 = growth2;
-        a.slice = pick_slice(Q, c.num_sms);
+        a.slice = xslice;
         const int grid = static_cast<int>(std::min<long long>((Q + a.slice - 1) / a.slice, 2LL * c.num_sms));
-        lv_solve<T><<<grid, 1024, 0, c.st>>>(a);
+        lv_solve<T><<<grid, level_threads(ps->max_level_tasks, a.slice), 0, c.st>>>(a);
         lv_store_x<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
-            c.L, c.n, c.r, static_cast<V_t*>(c.x), tr ? c.pnum : c.q, tr ? 1 : 0, Rs, lpad, c.sysidx, X);
+            c.L, c.n, c.r, static_cast<V_t*>(c.x), tr ? c.pnum : c.q, tr ? 1 : 0, Rs, r_row, r_sys, c.sysidx, X,
+            x_row, x_col);
     }
     if (!chk(cudaGetLastError(), "level kernels")) {
         cleanup();

@@ -107,6 +107,7 @@ struct NumericBatch {
     Symbolic* sym = nullptr;
     int is_complex = 0, regime = 0, L = 0, live = 0;
     int64_t lpad = 0;  // level regime: padded batch stride
+    int sysmajor = 0;  // level regime: V[system][slot] instead of V[slot][system] (kernels_level.cuh)
     DevBuf V, Rs;
     std::vector<uint8_t> freed;
 };
@@ -493,6 +494,7 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
         lc.V = op.batch->V.p;
         lc.Rs = op.batch->Rs.as<double>();
         lc.lpad = op.batch->lpad;
+        lc.sysmajor = op.batch->sysmajor;
         lc.Lstore = op.batch->L;
     }
     LevelProg *pf = nullptr, *ps = nullptr;
@@ -525,6 +527,7 @@ static int new_batch(Symbolic* S, int cx, int L, NumericBatch** out) {
     nb->freed.assign(L, 0);
     const size_t vsz = cx ? 16 : 8;
     nb->lpad = (L + 31) / 32 * 32;
+    nb->sysmajor = (sd.regime != 0 && want_sysmajor(L, num_sms())) ? 1 : 0;
     const size_t nsys = sd.regime == 0 ? static_cast<size_t>(L) : static_cast<size_t>(nb->lpad);
     CUDA_OK(nb->V.alloc(nsys * sd.lay.n_val * vsz));
     CUDA_OK(nb->Rs.alloc(nsys * sd.lay.n * sizeof(double)));
