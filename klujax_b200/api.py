@@ -13,6 +13,7 @@ library or a GPU these functions raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Callable
 
 import numpy as np
@@ -269,13 +270,14 @@ def analyze(Ai: Any, Aj: Any, n_col: int) -> KLUHandleManager:
 
 
 _PIPELINE_MIN_SYSTEMS = 8192   # host-resident batches at least this large are streamed in chunks
-_PIPELINE_CHUNKS = 16
+_PIPELINE_CHUNKS = int(os.environ.get("KLUJAX_PIPELINE_CHUNKS", "16"))
+_PIPELINE_STREAMS = int(os.environ.get("KLUJAX_PIPELINE_STREAMS", "2"))
 _streams: dict = {}
 
 
 def _copy_streams(dev: torch.device):
     if dev not in _streams:
-        _streams[dev] = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        _streams[dev] = [torch.cuda.Stream(device=dev) for _ in range(max(1, _PIPELINE_STREAMS))]
     return _streams[dev]
 
 
@@ -324,7 +326,7 @@ def _solve_symbol(fn: str, Ai, Aj, Ax, b, symbolic, check: bool, out=None):
             s.wait_stream(cur)
         for k in range(_PIPELINE_CHUNKS):
             lo, hi = bounds[k], bounds[k + 1]
-            s = streams[k % 2]
+            s = streams[k % len(streams)]
             with torch.cuda.stream(s):
                 Ax_d[lo:hi].copy_(Ax_t[lo:hi], non_blocking=True)
                 b_d[lo:hi].copy_(b_t[lo:hi], non_blocking=True)
@@ -336,8 +338,8 @@ def _solve_symbol(fn: str, Ai, Aj, Ax, b, symbolic, check: bool, out=None):
         for s in streams:
             cur.wait_stream(s)
         for t in (Ax_d, b_d, x, st, gr, Ai_d, Aj_d):
-            t.record_stream(streams[0])
-            t.record_stream(streams[1])
+            for s in streams:
+                t.record_stream(s)
     if check and _reseed_failed_certificates(fn, cx, Ai_t, Aj_t, Ax_d, b_d, x, st, gr, n):
         if out_v is not None:
             out_v.copy_(x, non_blocking=True)
