@@ -138,6 +138,7 @@ struct SmallArgs {
     int W;                   // systems (= consumer warps) per CTA
     int n, n_val, n_slots, zero_slot, rc, nz, flags;
     const int* coo_dst;      // [nz] slot of each COO entry of this call, -1 = not in pattern
+    const int* remap;        // compacted programs (plan.hpp: TaskProgram::remap): layout slot -> slot, else null
     const int* pattern_bad;  // device flag set by the COO map
     const int* rs_ptr;       // [n+1] row lists (original row order)
     const int* rs_slot;

@@ -10,7 +10,7 @@
 //
 // Replaces the same reference loops as kernels_small.cuh (/root/reference/klujax.cpp:431-451
 // and siblings).  Stream: per 128-lane step one header line (per lane
-// out<<18 | pivot-or-ONE<<4 | kind, kind 0 = idle lane) and P operand lines (a<<18 | b<<4,
+// out<<18 | pivot-or-ONE<<4 | fresh<<3 | kind, kind 0 = idle lane) and P operand lines (a<<18 | b<<4,
 // 0 = nothing); ctrl[step] = P | level-ends<<4.
 #pragma once
 #include <cstdint>
@@ -23,6 +23,7 @@ namespace kb {
 #ifndef KW_UNCOND
 #define KW_UNCOND 1
 #endif
+constexpr int kMaxWideSystems = 6;  // systems per CTA: 25 warps, 72 registers per thread (no spills)
 constexpr int kWarpsPerSystem = 4;
 constexpr int kLanesPerSystem = 32 * kWarpsPerSystem;
 constexpr int kStepBytes = kLanesPerSystem * 8;           // one step of one system's lanes
@@ -35,7 +36,7 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32 * (kWarpsPerSystem * 5 + 1), 1)
+__global__ void __launch_bounds__(32 * (kWarpsPerSystem * kMaxWideSystems + 1), 1)
     wide_kernel(const __grid_constant__ SmallArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
@@ -124,8 +125,11 @@ __global__ void __launch_bounds__(32 * (kWarpsPerSystem * 5 + 1), 1)
                     }
                 }
                 for (int e = tid; e < a.nz; e += kLanesPerSystem) {
-                    const int d = __ldg(a.coo_dst + e);
-                    if (d >= 0) S::st(V + d, Am[e]);
+                    int d = __ldg(a.coo_dst + e);
+                    if (d >= 0) {
+                        if (a.remap) d = __ldg(a.remap + d);
+                        S::st(V + d, Am[e]);
+                    }
                 }
                 named_barrier(bar_id, kLanesPerSystem);
                 // max-abs row scaling (KLU scale = 2): Rs in original row order
@@ -196,10 +200,11 @@ __global__ void __launch_bounds__(32 * (kWarpsPerSystem * 5 + 1), 1)
                     const uint32_t h = p[0];
                     const uint32_t w1 = p[kLanesPerSystem];  // first operand word (garbage if P == 0: unused)
                     cw = a.ctrl[pi][s + 1];                  // next step's control word, off the critical path
-                    const uint32_t kind = h & 0xFu;
+                    const uint32_t kind = h & 0x7u;
                     if (kind) {
                         V_t* po = reinterpret_cast<V_t*>(Vb + ((h >> (14 + SHR)) & MSK));
-                        V_t t = *po;
+                        V_t t = S::zero();
+                        if (!(h & 8u)) t = *po;  // 8: first write of a recycled slot starts from 0
 #if KW_UNCOND
                         if (P >= 1) {  // lanes without a pair multiply ZERO by ZERO: no lane-dependent branch
 #else

@@ -68,10 +68,10 @@ struct DevBuf {
 };
 
 struct SmallProg {
-    DevBuf stream;
+    DevBuf stream, remap, rs_slot;  // remap / rs_slot: compacted programs only
     std::vector<uint32_t> ctrl;
     std::vector<uint16_t> chunk_ptr;
-    int nchunks = 0, nbatch = 0, n_slots = 0, zero_slot = 0, nlevels = 0;
+    int nchunks = 0, nbatch = 0, n_slots = 0, zero_slot = 0, nlevels = 0, n_val = 0;
     int64_t n_mac = 0;
 };
 
@@ -237,9 +237,9 @@ static int ensure_seeded_dev(Symbolic* S, int cx, int nz, const int32_t* Ai_dev,
 // ---------------------------------------------------------------------------
 // program caches
 // ---------------------------------------------------------------------------
-static int get_small_prog(Symbolic* S, int cx, int mode, int rc, bool wide, SmallProg** out) {
+static int get_small_prog(Symbolic* S, int cx, int mode, int rc, bool wide, bool compact, SmallProg** out) {
     Seeded& sd = S->seeded[cx];
-    auto key = std::make_pair(mode, rc + (wide ? 1000 : 0));
+    auto key = std::make_pair(mode, rc + (wide ? 1000 : 0) + (compact ? 100000 : 0));
     auto it = sd.small.find(key);
     if (it == sd.small.end()) {
         TaskProgram tp;
@@ -250,7 +250,7 @@ static int get_small_prog(Symbolic* S, int cx, int mode, int rc, bool wide, Smal
             split = 111;  // one multiply-add per partial update (measured best: 11 < 14 < 24 < 47)
             if (const char* e = std::getenv("KLUJAX_CUDA_WIDE_GROUP")) split = 100 + std::atoi(e);
         }
-        build_program(S->ord, sd.piv, sd.lay, mode, rc, tp, split);
+        build_program(S->ord, sd.piv, sd.lay, mode, rc, tp, split, compact);
         if (!(wide ? pack_program_wide(sd.lay, tp, pp, cx ? 16 : 8) : pack_program(sd.lay, tp, pp))) return fail(KLU_TOO_LARGE, "program does not fit the shared-memory regime");
         auto sp = std::make_unique<SmallProg>();
         CUDA_OK(sp->stream.upload(pp.stream));
@@ -262,6 +262,13 @@ static int get_small_prog(Symbolic* S, int cx, int mode, int rc, bool wide, Smal
         sp->zero_slot = pp.zero_slot;
         sp->nlevels = tp.nlevels;
         sp->n_mac = tp.n_mac;
+        sp->n_val = tp.n_val;
+        if (!tp.remap.empty()) {
+            CUDA_OK(sp->remap.upload(tp.remap));
+            std::vector<int> rs(sd.lay.rs_slot.size());
+            for (size_t q = 0; q < rs.size(); ++q) rs[q] = tp.remap[sd.lay.rs_slot[q]];
+            CUDA_OK(sp->rs_slot.upload(rs));
+        }
         it = sd.small.emplace(key, std::move(sp)).first;
     }
     *out = it->second.get();
@@ -347,10 +354,14 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
         wide = fit <= 8;
         if (const char* ev = std::getenv("KLUJAX_CUDA_WIDE")) wide = std::atoi(ev) != 0;
     }
-    int e = get_small_prog(S, cx, op.mode, rc, wide, &p0);
+    // Fused factor + solve that keeps nothing: the program recycles dead value slots
+    // (plan.hpp: TaskProgram::remap), so more systems fit in shared memory.
+    bool compact = wide && factor && solve && !op.store_numeric && op.r <= rc;
+    if (const char* ev = std::getenv("KLUJAX_CUDA_COMPACT")) compact = compact && std::atoi(ev) != 0;
+    int e = get_small_prog(S, cx, op.mode, rc, wide, compact, &p0);
     if (e) return e;
     if (solve && op.r > rc) {
-        e = get_small_prog(S, cx, transpose ? PM_TSOLVE : PM_SOLVE, rc, wide, &p1);
+        e = get_small_prog(S, cx, transpose ? PM_TSOLVE : PM_SOLVE, rc, wide, false, &p1);
         if (e) return e;
     }
     static thread_local SmallArgs a;  // ~14 KB of parameters: control words travel by value
@@ -368,7 +379,7 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
         std::copy(p1->chunk_ptr.begin(), p1->chunk_ptr.end(), a.chunk_ptr[1]);
     }
     a.n = n;
-    a.n_val = sd.lay.n_val;
+    a.n_val = p0->n_val;
     a.n_slots = p0->n_slots;
     a.zero_slot = p0->zero_slot;
     a.rc = rc;
@@ -379,7 +390,8 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     a.coo_dst = S->cur->coo_dst.as<int>();
     a.pattern_bad = S->cur->bad.as<int>();
     a.rs_ptr = sd.d_rs_ptr.as<int>();
-    a.rs_slot = sd.d_rs_slot.as<int>();
+    a.rs_slot = p0->rs_slot.p ? p0->rs_slot.as<int>() : sd.d_rs_slot.as<int>();
+    a.remap = p0->remap.p ? p0->remap.as<int>() : nullptr;
     a.in_perm = transpose ? sd.d_q.as<int>() : sd.d_pnum.as<int>();
     a.out_perm = transpose ? sd.d_pnum.as<int>() : sd.d_q.as<int>();
     a.Ax = op.Ax;
@@ -401,7 +413,7 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     // at most 5 systems per CTA (thread limit), several CTAs per SM when systems are small.
     const size_t per_sys = wide ? ((static_cast<size_t>(a.n_slots) * vsz + n * 8ull + 16 + 15) & ~size_t(15))
                                 : ((static_cast<size_t>(a.n_slots) * vsz + n * 8ull + 15) & ~size_t(15));
-    int W = static_cast<int>(std::min<size_t>(wide ? 5 : 16, (kMaxDynSmem - kSmallHeaderBytes) / per_sys));
+    int W = static_cast<int>(std::min<size_t>(wide ? kMaxWideSystems : 16, (kMaxDynSmem - kSmallHeaderBytes) / per_sys));
     if (W < 1) return fail(KLU_TOO_LARGE, "system does not fit the shared-memory regime");
     const int sms = num_sms();
     while (W > 1 && (op.L + W - 1) / W < sms) --W;  // small batches: spread over all SMs first

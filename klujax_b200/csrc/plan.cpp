@@ -296,14 +296,77 @@ void rebalance_levels(TaskProgram& prog, int n_val, int lanes) {
     for (int l = 0; l < nl; ++l) prog.level_ptr[l + 1] += prog.level_ptr[l];
 }
 
+// Linear-scan slot allocation over the level sets (see TaskProgram::remap).
+void compact_slots(const SlotLayout& lay, TaskProgram& prog) {
+    const int nv = lay.n_val, nl = prog.nlevels;
+    const int NEVER = 1 << 30;
+    std::vector<int> birth(nv, NEVER), death(nv, 0), first_write(nv, -1);
+    for (int s = 0; s < nv; ++s)
+        if (lay.slot_csc[s] >= 0) birth[s] = 0;  // scattered (and row-scaled) before level 1
+    for (size_t ti = 0; ti < prog.tasks.size(); ++ti) {
+        const Task& t = prog.tasks[ti];
+        auto use = [&](int s, bool write) {
+            if (s >= nv) return;
+            if (birth[s] == NEVER) {
+                // fill-in: born at its first write; a read before any write means the value
+                // must be the zero of the load phase
+                birth[s] = write ? t.level : 0;
+                if (write) first_write[s] = static_cast<int>(ti);
+            }
+            death[s] = std::max(death[s], t.level);
+        };
+        for (int q = 0; q < t.plen; ++q) {
+            use(prog.pa[t.pbeg + q], false);
+            use(prog.pb[t.pbeg + q], false);
+        }
+        if (t.div >= 0) use(t.div, false);
+        use(t.out, true);
+    }
+    for (int s = 0; s < nv; ++s)
+        if (birth[s] == NEVER) birth[s] = 0;  // never touched by a task: only the load phase sees it
+    // slots by birth level; slots that die at level d are free again from level d + 1
+    std::vector<std::vector<int>> born(nl + 2), dies(nl + 2);
+    for (int s = 0; s < nv; ++s) {
+        born[std::min(birth[s], nl + 1)].push_back(s);
+        dies[std::min(death[s], nl + 1)].push_back(s);
+    }
+    prog.remap.assign(nv, -1);
+    std::vector<int> free_ids;  // kept sorted descending: pop_back gives the smallest id
+    int n_phys = 0;
+    for (int l = 0; l <= nl + 1; ++l) {
+        if (l >= 1) {
+            for (int s : dies[l - 1]) free_ids.push_back(prog.remap[s]);
+            std::sort(free_ids.begin(), free_ids.end(), std::greater<int>());
+        }
+        for (int s : born[l]) {
+            if (l == 0 || free_ids.empty()) {
+                prog.remap[s] = n_phys++;
+            } else {
+                prog.remap[s] = free_ids.back();
+                free_ids.pop_back();
+            }
+            if (l >= 1 && first_write[s] >= 0) prog.tasks[first_write[s]].fresh = 1;
+        }
+    }
+    auto rn = [&](int s) { return s < nv ? prog.remap[s] : s - nv + n_phys; };
+    for (Task& t : prog.tasks) {
+        t.out = rn(t.out);
+        if (t.div >= 0) t.div = rn(t.div);
+    }
+    for (int& s : prog.pa) s = rn(s);
+    for (int& s : prog.pb) s = rn(s);
+    prog.n_val = n_phys;
+}
+
 }  // namespace
 
 void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
-                   int rc, TaskProgram& prog, int split) {
+                   int rc, TaskProgram& prog, int split, bool compact) {
     const int n = lay.n;
     prog = TaskProgram();
     prog.mode = mode;
     prog.rc = rc;
+    prog.n_val = lay.n_val;
     const bool do_factor = (mode == PM_FACTOR || mode == PM_FACTOR_SOLVE || mode == PM_FACTOR_TSOLVE);
     const bool do_solve = (mode == PM_FACTOR_SOLVE || mode == PM_SOLVE);
     const bool do_tsolve = (mode == PM_FACTOR_TSOLVE || mode == PM_TSOLVE);
@@ -441,13 +504,14 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
     if (split >= 100 && do_factor &&
         !(std::getenv("KLUJAX_CUDA_REBALANCE") && std::atoi(std::getenv("KLUJAX_CUDA_REBALANCE")) == 0))
         rebalance_levels(prog, lay.n_val, 128);
+    if (compact && do_factor && (do_solve || do_tsolve)) compact_slots(lay, prog);
 }
 
 bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out) {
     out = PackedProgram();
     constexpr int LW = 32, LINES = kChunkWords / LW;
     const int nx = (prog.mode == PM_FACTOR) ? 0 : lay.n * prog.rc;
-    out.zero_slot = lay.n_val + nx;  // then ONE (= 1), then TRASH (write-only)
+    out.zero_slot = prog.n_val + nx;  // then ONE (= 1), then TRASH (write-only)
     out.n_slots = out.zero_slot + 3;
     if (out.n_slots > 16383) return false;
     const uint32_t ZERO = out.zero_slot, ONE = ZERO + 1, TRASH = ZERO + 2;
@@ -612,7 +676,7 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
     constexpr int LANES = 128;
     const bool bank_order = !(std::getenv("KLUJAX_CUDA_BANK_ORDER") && std::atoi(std::getenv("KLUJAX_CUDA_BANK_ORDER")) == 0);
     const int nx = (prog.mode == PM_FACTOR) ? 0 : lay.n * prog.rc;
-    out.zero_slot = lay.n_val + nx;  // then ONE (= 1), then TRASH
+    out.zero_slot = prog.n_val + nx;  // then ONE (= 1), then TRASH
     out.n_slots = out.zero_slot + 3;
     if (out.n_slots > 16383) return false;
     const uint32_t ZERO = out.zero_slot, ONE = out.zero_slot + 1;
@@ -644,7 +708,7 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
                 const Task& tk = prog.tasks[order[i + k]];
                 const uint32_t d = tk.div >= 0 ? static_cast<uint32_t>(tk.div) : ONE;
                 const uint32_t kind = tk.kind == TK_RECIP ? 4u : tk.kind == TK_MUL_TRACK ? 3u : tk.kind == TK_MUL ? 2u : 1u;
-                base[k] = (static_cast<uint32_t>(tk.out) << 18) | (d << 4) | kind;
+                base[k] = (static_cast<uint32_t>(tk.out) << 18) | (d << 4) | (tk.fresh ? 8u : 0u) | kind;
                 for (int q = 0; q < P; ++q)
                     base[LANES * (1 + q) + k] =
                         q < tk.plen ? (static_cast<uint32_t>(prog.pa[tk.pbeg + q]) << 18) |

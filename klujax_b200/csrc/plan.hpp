@@ -33,6 +33,7 @@ struct Task {
     int pbeg = 0, plen = 0;
     int level = 0;
     uint8_t kind = TK_SUB;
+    uint8_t fresh = 0;  // first write of a recycled slot: start from 0, not from the old content
 };
 
 // Slot layout of one system's value array.
@@ -69,11 +70,19 @@ struct TaskProgram {
     std::vector<int> level_ptr;    // nlevels+1
     std::vector<int> pa, pb;       // operand pairs
     int64_t n_mac = 0;
+    // Slot compaction (programs that do not keep the factors: fused factor + solve).  A value
+    // slot is live from its first write (level 0 for the entries of A) to its last use; dead
+    // slots are recycled for fill-in that is born later, so the value array a system needs in
+    // shared memory shrinks to the peak number of live values.  n_val = value slots the
+    // program addresses (X follows at n_val); remap[s] = physical slot of layout slot s
+    // (empty = identity, n_val = lay.n_val).
+    int n_val = 0;
+    std::vector<int> remap;
 };
 
 void build_layout(const CscPattern& A, const Ordering& ord, const PivotPlan& piv, SlotLayout& lay);
 void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
-                   int rc, TaskProgram& prog, int split = 0);
+                   int rc, TaskProgram& prog, int split = 0, bool compact = false);
 
 // Packed schedule of the shared-memory (small-matrix) regime: one warp per system.
 //
