@@ -96,7 +96,7 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
 //        header line  : out<<18 | (pivot slot or ONE)<<4 | is-pivot<<1 | is-L-entry
 //        2*trips operand lines: a<<18 | b<<4
 //    Idle lanes multiply the ZERO slot and write to the TRASH slot: no lane-dependent branch.
-constexpr int kChunkWords = 1024;
+constexpr int kChunkWords = 2048;
 constexpr int kMaxBatches = 1536;  // per program (control words live in the parameter space)
 constexpr int kMaxChunks = 255;
 constexpr uint32_t kCwPivot = 1u << 11, kCwMul = 1u << 12, kCwTrack = 1u << 13;
