@@ -297,7 +297,7 @@ void rebalance_levels(TaskProgram& prog, int n_val, int lanes) {
 }
 
 // Linear-scan slot allocation over the level sets (see TaskProgram::remap).
-void compact_slots(const SlotLayout& lay, TaskProgram& prog) {
+void compact_slots(const SlotLayout& lay, TaskProgram& prog, int bank_cols) {
     const int nv = lay.n_val, nl = prog.nlevels;
     const int NEVER = 1 << 30;
     std::vector<int> birth(nv, NEVER), death(nv, 0), first_write(nv, -1);
@@ -331,20 +331,34 @@ void compact_slots(const SlotLayout& lay, TaskProgram& prog) {
         dies[std::min(death[s], nl + 1)].push_back(s);
     }
     prog.remap.assign(nv, -1);
-    std::vector<int> free_ids;  // kept sorted descending: pop_back gives the smallest id
+    // A slot keeps its shared-memory bank column (slot mod bank_cols): the layout numbers the
+    // entries of a column consecutively, which is what keeps the lanes of a dense level in
+    // different banks, and the packer's lane order was chosen for those columns.  Free ids are
+    // kept per bank column (sorted descending: pop_back gives the smallest).
+    const int G = std::max(1, bank_cols);
+    std::vector<std::vector<int>> free_ids(G);
     int n_phys = 0;
+    auto take = [&](int col) {
+        std::vector<int>& f = free_ids[col];
+        if (!f.empty()) {
+            const int id = f.back();
+            f.pop_back();
+            return id;
+        }
+        while (n_phys % G != col) {  // ids skipped on the way become free ids of their columns
+            std::vector<int>& h = free_ids[n_phys % G];
+            h.insert(h.begin(), n_phys);  // larger than every id in the list: keeps it descending
+            ++n_phys;
+        }
+        return n_phys++;
+    };
     for (int l = 0; l <= nl + 1; ++l) {
         if (l >= 1) {
-            for (int s : dies[l - 1]) free_ids.push_back(prog.remap[s]);
-            std::sort(free_ids.begin(), free_ids.end(), std::greater<int>());
+            for (int s : dies[l - 1]) free_ids[prog.remap[s] % G].push_back(prog.remap[s]);
+            for (auto& f : free_ids) std::sort(f.begin(), f.end(), std::greater<int>());
         }
         for (int s : born[l]) {
-            if (l == 0 || free_ids.empty()) {
-                prog.remap[s] = n_phys++;
-            } else {
-                prog.remap[s] = free_ids.back();
-                free_ids.pop_back();
-            }
+            prog.remap[s] = take(s % G);
             if (l >= 1 && first_write[s] >= 0) prog.tasks[first_write[s]].fresh = 1;
         }
     }
@@ -361,7 +375,7 @@ void compact_slots(const SlotLayout& lay, TaskProgram& prog) {
 }  // namespace
 
 void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
-                   int rc, TaskProgram& prog, int split, bool compact) {
+                   int rc, TaskProgram& prog, int split, int compact) {
     const int n = lay.n;
     prog = TaskProgram();
     prog.mode = mode;
@@ -504,7 +518,7 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
     if (split >= 100 && do_factor &&
         !(std::getenv("KLUJAX_CUDA_REBALANCE") && std::atoi(std::getenv("KLUJAX_CUDA_REBALANCE")) == 0))
         rebalance_levels(prog, lay.n_val, 128);
-    if (compact && do_factor && (do_solve || do_tsolve)) compact_slots(lay, prog);
+    if (compact && do_factor && (do_solve || do_tsolve)) compact_slots(lay, prog, compact);
 }
 
 bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out) {

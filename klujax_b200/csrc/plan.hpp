@@ -81,8 +81,10 @@ struct TaskProgram {
 };
 
 void build_layout(const CscPattern& A, const Ordering& ord, const PivotPlan& piv, SlotLayout& lay);
+// compact: 0 = keep the layout's slots; else recycle dead slots (TaskProgram::remap), keeping
+// every slot in its shared-memory bank column modulo `compact` (8 for 16-byte, 16 for 8-byte values)
 void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
-                   int rc, TaskProgram& prog, int split = 0, bool compact = false);
+                   int rc, TaskProgram& prog, int split = 0, int compact = 0);
 
 // Packed schedule of the shared-memory (small-matrix) regime: one warp per system.
 //
