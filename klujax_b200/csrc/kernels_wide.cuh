@@ -10,8 +10,8 @@
 //
 // Replaces the same reference loops as kernels_small.cuh (/root/reference/klujax.cpp:431-451
 // and siblings).  Stream: per 128-lane step one header line (per lane
-// out<<18 | pivot-or-ONE<<4 | fresh<<3 | kind, kind 0 = idle lane) and P operand lines (a<<18 | b<<4,
-// 0 = nothing); ctrl[step] = P | level-ends<<4.
+// out<<18 | pivot-or-ONE<<4 | fresh<<3 | kind, kind 0 = idle lane) and ONE operand line
+// (a<<18 | b<<4; ZERO, ZERO for a lane without a pair); ctrl[step] = 1 | level-ends<<4.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -20,9 +20,6 @@
 
 namespace kb {
 
-#ifndef KW_UNCOND
-#define KW_UNCOND 1
-#endif
 constexpr int kMaxWideSystems = 6;  // systems per CTA: 25 warps, 72 registers per thread (no spills)
 constexpr int kWarpsPerSystem = 4;
 constexpr int kLanesPerSystem = 32 * kWarpsPerSystem;
@@ -195,30 +192,18 @@ __global__ void __launch_bounds__(32 * (kWarpsPerSystem * kMaxWideSystems + 1), 
                 const int s0 = a.chunk_ptr[pi][c], s1 = a.chunk_ptr[pi][c + 1];
                 uint32_t cw = a.ctrl[pi][s0];
                 for (int s = s0; s < s1; ++s) {
-                    const int P = cw & 0xF;
                     const bool level_end = (cw & 16u) != 0;
                     const uint32_t h = p[0];
-                    const uint32_t w1 = p[kLanesPerSystem];  // first operand word (garbage if P == 0: unused)
+                    const uint32_t w1 = p[kLanesPerSystem];  // the step's operand line
                     cw = a.ctrl[pi][s + 1];                  // next step's control word, off the critical path
                     const uint32_t kind = h & 0x7u;
                     if (kind) {
                         V_t* po = reinterpret_cast<V_t*>(Vb + ((h >> (14 + SHR)) & MSK));
                         V_t t = S::zero();
                         if (!(h & 8u)) t = *po;  // 8: first write of a recycled slot starts from 0
-#if KW_UNCOND
-                        if (P >= 1) {  // lanes without a pair multiply ZERO by ZERO: no lane-dependent branch
-#else
-                        if (P >= 1 && w1) {
-#endif
+                        {   // lanes without a pair multiply ZERO by ZERO: no lane-dependent branch
                             const V_t va = *reinterpret_cast<const V_t*>(Vb + ((w1 >> (14 + SHR)) & MSK));
                             const V_t vb = *reinterpret_cast<const V_t*>(Vb + ((w1 >> SHR) & MSK));
-                            S::fms_acc(t, va, vb);
-                        }
-#pragma unroll 1
-                        for (int q = 2; q <= P; ++q) {
-                            const uint32_t w = p[q * kLanesPerSystem];
-                            const V_t va = *reinterpret_cast<const V_t*>(Vb + ((w >> (14 + SHR)) & MSK));
-                            const V_t vb = *reinterpret_cast<const V_t*>(Vb + ((w >> SHR) & MSK));
                             S::fms_acc(t, va, vb);
                         }
                         if (kind >= WK_MUL) {
@@ -232,7 +217,7 @@ __global__ void __launch_bounds__(32 * (kWarpsPerSystem * kMaxWideSystems + 1), 
                         }
                         *po = t;
                     }
-                    p += (1 + P) * kLanesPerSystem;
+                    p += 2 * kLanesPerSystem;  // a step = header line + one operand line
                     if (level_end) named_barrier(bar_id, kLanesPerSystem);
                 }
                 __syncwarp();

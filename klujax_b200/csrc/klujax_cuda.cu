@@ -247,8 +247,8 @@ static int get_small_prog(Symbolic* S, int cx, int mode, int rc, bool wide, bool
         int split = 0;  // measured: the dot form beats as-soon-as-possible solve updates here (220k vs 234k cycles)
         if (const char* e = std::getenv("KLUJAX_CUDA_SPLIT")) split = std::atoi(e);
         if (wide) {
-            split = 111;  // one multiply-add per partial update (measured best: 11 < 14 < 24 < 47)
-            if (const char* e = std::getenv("KLUJAX_CUDA_WIDE_GROUP")) split = 100 + std::atoi(e);
+            split = 111;  // one multiply-add per partial update (measured best: 11 < 14 < 24 < 47;
+                          // the kernel's step format is fixed to it)
         }
         build_program(S->ord, sd.piv, sd.lay, mode, rc, tp, split, compact ? (cx ? 8 : 16) : 0);
         if (!(wide ? pack_program_wide(sd.lay, tp, pp, cx ? 16 : 8) : pack_program(sd.lay, tp, pp))) return fail(KLU_TOO_LARGE, "program does not fit the shared-memory regime");

@@ -712,9 +712,10 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
         if (bank_order) order_for_banks(prog, order, 128 / elem_bytes);
         for (size_t i = 0; i < order.size(); i += LANES) {
             const size_t cnt = std::min<size_t>(LANES, order.size() - i);
-            int P = 0;
-            for (size_t k = 0; k < cnt; ++k) P = std::max(P, prog.tasks[order[i + k]].plen);
-            if (P > 7) return false;
+            // the kernel's step format is fixed: header line + ONE operand line (split 111)
+            for (size_t k = 0; k < cnt; ++k)
+                if (prog.tasks[order[i + k]].plen > 1) return false;
+            const int P = 1;
             const int words = LANES * (1 + P);
             if (used + words > kChunkWords) open_chunk();
             uint32_t* base = out.stream.data() + chunk_base + used;
