@@ -416,7 +416,7 @@ def main():
                                w.name, "lv_factor/lv_solve (whole step timed)"),
                 "algorithmic_bytes_per_system": w.algorithmic_bytes_per_system(nnz_lu)}
     if w.name == "cfg5":  # what actually binds (ncu, profiles/README.md): on-chip, not HBM
-        roofline["binding_resource"] = ("shared-memory wavefronts ~63% of peak and issue slots ~52% busy "
+        roofline["binding_resource"] = ("shared-memory wavefronts ~67% of peak and issue slots ~51% busy "
                                         "(ncu --set full, profiles/): the on-chip pipes of the SM with six "
                                         "resident systems, not HBM")
     tr = os.path.join(ROOT, "profiles", "traffic.json")
