@@ -359,11 +359,17 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     bool compact = wide && factor && solve && !op.store_numeric && op.r <= rc;
     if (const char* ev = std::getenv("KLUJAX_CUDA_COMPACT")) compact = compact && std::atoi(ev) != 0;
     int e = get_small_prog(S, cx, op.mode, rc, wide, compact, &p0);
-    if (e) return e;
-    if (solve && op.r > rc) {
-        e = get_small_prog(S, cx, transpose ? PM_TSOLVE : PM_SOLVE, rc, wide, false, &p1);
-        if (e) return e;
+    if (!e && solve && op.r > rc) e = get_small_prog(S, cx, transpose ? PM_TSOLVE : PM_SOLVE, rc, wide, false, &p1);
+    if (e == KLU_TOO_LARGE && wide) {
+        // the single-multiply-add schedule of the multi-warp kernel has too many steps for the
+        // control-word table (large n): the one-warp kernel's dot-form schedule packed at
+        // seeding time, so it is the fallback inside this regime
+        wide = false;
+        p0 = p1 = nullptr;
+        e = get_small_prog(S, cx, op.mode, rc, false, false, &p0);
+        if (!e && solve && op.r > rc) e = get_small_prog(S, cx, transpose ? PM_TSOLVE : PM_SOLVE, rc, false, false, &p1);
     }
+    if (e) return e;
     static thread_local SmallArgs a;  // ~14 KB of parameters: control words travel by value
     std::memset(&a, 0, sizeof(a));
     a.stream[0] = p0->stream.as<uint32_t>();

@@ -616,3 +616,23 @@ def test_cfg3_full_grid_properties(K):
     res = torch.linalg.vector_norm(K.dot(Ai, Aj, Ax, x) - b, dim=1) / torch.linalg.vector_norm(b, dim=1)
     assert float(res.max()) < RES_TOL
     assert float((x2 - (x[:, :, :1] - 2.0 * x[:, :, 1:2])).abs().max() / x.abs().max()) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [256, 320])
+def test_large_shared_memory_systems(K, oracle, n):
+    """Systems that fill most of an SM's shared memory (one or two resident systems): n = 256
+    still packs for the multi-warp kernel, n = 320 exceeds its control-word table and falls back
+    to the one-warp kernel inside the same regime."""
+    pat = synth.SaxPattern(n, seed=4)
+    L = 5
+    Ax = pat.values(0, L)
+    b = np.random.default_rng(8).standard_normal((L, n, 1)) + 0j
+    so = oracle.analyze(pat.Ai, pat.Aj, n)
+    ref = oracle.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, so)
+    oracle.free_symbolic(so)
+    with K.analyze(pat.Ai, pat.Aj, n) as sym:
+        x = np_(K.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, sym))
+        st, gr = K.last_status()
+        assert int(st.abs().max()) == 0
+    assert relerr(x, ref) < X_TOL
