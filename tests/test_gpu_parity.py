@@ -636,3 +636,71 @@ def test_large_shared_memory_systems(K, oracle, n):
         st, gr = K.last_status()
         assert int(st.abs().max()) == 0
     assert relerr(x, ref) < X_TOL
+
+
+@pytest.mark.gpu
+def test_fuzz_structures_both_small_kernels(K, oracle, monkeypatch):
+    """Seeded fuzz over structures the schedule passes (step balancing, bank-aware lane order,
+    slot compaction) have to survive: random sparse patterns with and without a dominant
+    diagonal, arrow-heads, block-triangular chains, dense small matrices; both dtypes, one and
+    several right-hand sides, both shared-memory kernels; x against the oracle."""
+    rng = np.random.default_rng(1234)
+
+    def pattern(kind, n):
+        A = np.zeros((n, n))
+        if kind == "random":
+            A = rng.standard_normal((n, n)) * (rng.random((n, n)) < min(0.5, 4.0 / n))
+        elif kind == "arrow":
+            A[0, :] = rng.standard_normal(n); A[:, 0] = rng.standard_normal(n)
+            A[-1, :] = rng.standard_normal(n)
+        elif kind == "btf":
+            k = 0
+            while k < n:
+                m = int(rng.integers(1, 9)); e = min(n, k + m)
+                A[k:e, k:e] = rng.standard_normal((e - k, e - k))
+                if e < n:
+                    A[k:e, e:] = rng.standard_normal((e - k, n - e)) * (rng.random((e - k, n - e)) < 0.1)
+                k = e
+        elif kind == "dense":
+            A = rng.standard_normal((n, n))
+        elif kind == "band":
+            for d in range(-3, 4):
+                A += np.diag(rng.standard_normal(n - abs(d)), d)
+        A[np.arange(n), np.arange(n)] = 0.0
+        A += np.diag(2.0 + np.abs(A).sum(1))
+        p = rng.permutation(n)
+        return A[p]  # rows permuted: the diagonal is hidden, the transversal has to find it
+
+    cases = [("random", 37), ("random", 90), ("arrow", 48), ("btf", 64), ("dense", 24), ("band", 120),
+             ("random", 150), ("btf", 130)]
+    for ci, (kind, n) in enumerate(cases):
+        A = pattern(kind, n)
+        Ai, Aj = (v.astype(np.int32) for v in np.nonzero(A))
+        for dtype in (np.float64, np.complex128):
+            L, r = (6, 1) if ci % 2 == 0 else (3, 5)
+            Ax = np.tile(A[Ai, Aj], (L, 1)) * (1.0 + 0.05 * rng.standard_normal((L, Ai.size)))
+            b = rng.standard_normal((L, n, r))
+            if dtype is np.complex128:
+                Ax = Ax * (1.0 + 0.1j)
+                b = b + 1j * rng.standard_normal((L, n, r))
+            so = oracle.analyze(Ai, Aj, n)
+            ref = oracle.solve_with_symbol(Ai, Aj, Ax, b, so)
+            reft = oracle.solve_with_symbol(Ai, Aj, Ax, b, so, transpose=True)
+            oracle.free_symbolic(so)
+            # The transversal need not recover the dominant diagonal of a row-permuted matrix,
+            # so KLU's tol = 1e-3 pivoting may run on small pivots: the bar is then the oracle's
+            # own distance from the dense LAPACK solution, not 1e-10.
+            true = np.stack([np.linalg.solve(dense(Ai, Aj, Ax[m], n), b[m]) for m in range(L)])
+            truet = np.stack([np.linalg.solve(dense(Ai, Aj, Ax[m], n).T, b[m]) for m in range(L)])
+            tol = max(X_TOL, 10.0 * relerr(ref, true))
+            tolt = max(X_TOL, 10.0 * relerr(reft, truet))
+            for wide in ("0", "1"):
+                monkeypatch.setenv("KLUJAX_CUDA_WIDE", wide)
+                with K.analyze(Ai, Aj, n) as sym:
+                    x = np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym))
+                    xt = np_(K.tsolve_with_symbol(Ai, Aj, Ax, b, sym))
+                    with K.factor(Ai, Aj, Ax, sym) as num:
+                        xn = np_(K.solve_with_numeric(num, b, sym))
+                assert relerr(x, ref) < tol and relerr(x, true) < tol, (kind, n, dtype, wide)
+                assert relerr(xt, reft) < tolt and relerr(xt, truet) < tolt, (kind, n, dtype, wide)
+                assert relerr(xn, ref) < tol, (kind, n, dtype, wide)
