@@ -639,11 +639,12 @@ def test_large_shared_memory_systems(K, oracle, n):
 
 
 @pytest.mark.gpu
-def test_fuzz_structures_both_small_kernels(K, oracle, monkeypatch):
+def test_fuzz_structures_all_kernels(K, oracle, monkeypatch):
     """Seeded fuzz over structures the schedule passes (step balancing, bank-aware lane order,
     slot compaction) have to survive: random sparse patterns with and without a dominant
     diagonal, arrow-heads, block-triangular chains, dense small matrices; both dtypes, one and
-    several right-hand sides, both shared-memory kernels; x against the oracle."""
+    several right-hand sides, both shared-memory kernels and the level-scheduled regime; x against
+    the oracle and dense LAPACK."""
     rng = np.random.default_rng(1234)
 
     def pattern(kind, n):
@@ -694,8 +695,12 @@ def test_fuzz_structures_both_small_kernels(K, oracle, monkeypatch):
             truet = np.stack([np.linalg.solve(dense(Ai, Aj, Ax[m], n).T, b[m]) for m in range(L)])
             tol = max(X_TOL, 10.0 * relerr(ref, true))
             tolt = max(X_TOL, 10.0 * relerr(reft, truet))
-            for wide in ("0", "1"):
-                monkeypatch.setenv("KLUJAX_CUDA_WIDE", wide)
+            for wide in ("0", "1", "level"):
+                if wide == "level":  # the level-scheduled regime on the same systems
+                    monkeypatch.setenv("KLUJAX_CUDA_FORCE_REGIME", "1")
+                else:
+                    monkeypatch.delenv("KLUJAX_CUDA_FORCE_REGIME", raising=False)
+                    monkeypatch.setenv("KLUJAX_CUDA_WIDE", wide)
                 with K.analyze(Ai, Aj, n) as sym:
                     x = np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym))
                     xt = np_(K.tsolve_with_symbol(Ai, Aj, Ax, b, sym))
