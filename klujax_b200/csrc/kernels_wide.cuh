@@ -9,9 +9,10 @@
 // cross-lane reductions, one named barrier (bar.sync id, 128) per level.
 //
 // Replaces the same reference loops as kernels_small.cuh (/root/reference/klujax.cpp:431-451
-// and siblings).  Stream: per 128-lane step one header line (per lane
-// out<<18 | pivot-or-ONE<<4 | fresh<<3 | kind, kind 0 = idle lane) and ONE operand line
-// (a<<18 | b<<4; ZERO, ZERO for a lane without a pair); ctrl[step] = 1 | level-ends<<4.
+// and siblings).  Stream: per 128-lane step and lane one header word
+// (out<<18 | pivot-or-ONE<<4 | fresh<<3 | kind, kind 0 = idle lane) and ONE operand word
+// (a<<18 | b<<4; ZERO, ZERO for a lane without a pair), stored as a pair (one 8-byte load);
+// ctrl[step] = 1 | level-ends<<4.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -188,13 +189,14 @@ __global__ void __launch_bounds__(32 * (kWarpsPerSystem * kMaxWideSystems + 1), 
             for (int c = 0; c < a.nchunks[pi]; ++c, ++cc) {
                 const uint32_t buf = cc % kRingBufs;
                 mbar_wait(full + buf, (cc / kRingBufs) & 1);
-                const uint32_t* p = reinterpret_cast<const uint32_t*>(ring + buf * kChunkBytes) + tid;
+                // a step = 128 (header word, operand word) pairs, one 8-byte load per lane
+                const uint2* p = reinterpret_cast<const uint2*>(ring + buf * kChunkBytes) + tid;
                 const int s0 = a.chunk_ptr[pi][c], s1 = a.chunk_ptr[pi][c + 1];
                 uint32_t cw = a.ctrl[pi][s0];
                 for (int s = s0; s < s1; ++s) {
                     const bool level_end = (cw & 16u) != 0;
-                    const uint32_t h = p[0];
-                    const uint32_t w1 = p[kLanesPerSystem];  // the step's operand line
+                    const uint2 hw = p[0];
+                    const uint32_t h = hw.x, w1 = hw.y;  // header word, operand word
                     cw = a.ctrl[pi][s + 1];                  // next step's control word, off the critical path
                     const uint32_t kind = h & 0x7u;
                     if (kind) {
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(32 * (kWarpsPerSystem * kMaxWideSystems + 1), 
                         }
                         *po = t;
                     }
-                    p += 2 * kLanesPerSystem;  // a step = header line + one operand line
+                    p += kLanesPerSystem;
                     if (level_end) named_barrier(bar_id, kLanesPerSystem);
                 }
                 __syncwarp();

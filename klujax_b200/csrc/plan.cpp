@@ -621,7 +621,7 @@ namespace kb {
 
 // Packs a bounded-group program (build_program with split = 100 + 10*min + max, max <= 7) for
 // the multi-warp shared-memory kernel (kernels_wide.cuh).  A level is cut into 128-lane steps;
-// a step is one header line (per lane: out<<18 | pivot-or-ONE<<4 | kind) and P operand lines
+// a step is, per lane, one header word (out<<18 | pivot-or-ONE<<4 | fresh<<3 | kind) and one operand word
 // (per lane: a<<18 | b<<4, 0 = nothing), P = longest task of the step (tasks are sorted by
 // length).  ctrl[step] = P | level-ends<<4; steps never straddle a chunk.
 namespace {
@@ -712,7 +712,7 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
         if (bank_order) order_for_banks(prog, order, 128 / elem_bytes);
         for (size_t i = 0; i < order.size(); i += LANES) {
             const size_t cnt = std::min<size_t>(LANES, order.size() - i);
-            // the kernel's step format is fixed: header line + ONE operand line (split 111)
+            // the kernel's step format is fixed: header word + ONE operand word per lane (split 111)
             for (size_t k = 0; k < cnt; ++k)
                 if (prog.tasks[order[i + k]].plen > 1) return false;
             const int P = 1;
@@ -723,12 +723,11 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
                 const Task& tk = prog.tasks[order[i + k]];
                 const uint32_t d = tk.div >= 0 ? static_cast<uint32_t>(tk.div) : ONE;
                 const uint32_t kind = tk.kind == TK_RECIP ? 4u : tk.kind == TK_MUL_TRACK ? 3u : tk.kind == TK_MUL ? 2u : 1u;
-                base[k] = (static_cast<uint32_t>(tk.out) << 18) | (d << 4) | (tk.fresh ? 8u : 0u) | kind;
-                for (int q = 0; q < P; ++q)
-                    base[LANES * (1 + q) + k] =
-                        q < tk.plen ? (static_cast<uint32_t>(prog.pa[tk.pbeg + q]) << 18) |
-                                          (static_cast<uint32_t>(prog.pb[tk.pbeg + q]) << 4)
-                                    : idle_op;
+                // lane k: (header word, operand word) side by side
+                base[2 * k] = (static_cast<uint32_t>(tk.out) << 18) | (d << 4) | (tk.fresh ? 8u : 0u) | kind;
+                base[2 * k + 1] = tk.plen ? (static_cast<uint32_t>(prog.pa[tk.pbeg]) << 18) |
+                                                (static_cast<uint32_t>(prog.pb[tk.pbeg]) << 4)
+                                          : idle_op;
             }
             const bool level_end = (i + LANES >= order.size());
             out.ctrl.push_back(static_cast<uint32_t>(P) | (level_end ? 16u : 0u));

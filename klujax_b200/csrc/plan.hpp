@@ -112,7 +112,7 @@ struct PackedProgram {
 };
 bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out);
 // multi-warp form (kernels_wide.cuh): ctrl[step] = P | level-ends<<4 for 128-lane steps of one
-// header line + P operand lines; chunk_ptr[c] = first step of chunk c; nbatch = steps
+// 128 (header word, operand word) pairs, one per lane; chunk_ptr[c] = first step of chunk c; nbatch = steps
 bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out, int elem_bytes = 16);
 
 }  // namespace kb
