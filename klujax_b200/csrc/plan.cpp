@@ -619,11 +619,11 @@ bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram&
 
 namespace kb {
 
-// Packs a bounded-group program (build_program with split = 100 + 10*min + max, max <= 7) for
-// the multi-warp shared-memory kernel (kernels_wide.cuh).  A level is cut into 128-lane steps;
-// a step is, per lane, one header word (out<<18 | pivot-or-ONE<<4 | fresh<<3 | kind) and one operand word
-// (per lane: a<<18 | b<<4, 0 = nothing), P = longest task of the step (tasks are sorted by
-// length).  ctrl[step] = P | level-ends<<4; steps never straddle a chunk.
+// Packs a single-multiply-add program (build_program with split = 111) for the multi-warp
+// shared-memory kernel (kernels_wide.cuh).  A level is cut into 128-lane steps; a step is, per
+// lane, one header word (out<<18 | pivot-or-ONE<<4 | fresh<<3 | kind) and one operand word
+// (a<<18 | b<<4; ZERO, ZERO for a lane without a pair), stored side by side.
+// ctrl[step] = 1 | level-ends<<4; steps never straddle a chunk.
 namespace {
 
 // Lane order of the tasks of one level for the multi-warp kernel.  A 16-byte (8-byte)
