@@ -281,13 +281,18 @@ static int get_level_prog(Symbolic* S, int cx, int mode, long long batch_cols, L
     // memory round trip, so every multiply-add is applied as soon as its operands are final
     // (split 2: cfg 4 refactor+solves 193 -> 40 ms per step); with thousands of columns the
     // kernels are traffic-bound and partial updates are grouped (>= 8 multiply-adds, split 3)
-    // or not split at all for the factorization (split 0).  Huge factorizations (cfg 3:
-    // 2.6e8 multiply-adds) always keep the dot form: one task per multiply-add would not fit.
+    // or not split at all for the factorization (split 0).  A factorization with millions of
+    // multiply-adds (cfg 1: 1.65e7 for n = 1000, cfg 3: 2.6e8) is never expanded into one task
+    // per multiply-add - the schedule alone would be hundreds of MB and seconds of host time
+    // (cfg 1 `solve`: 3.2 s per call) - but into groups of >= 8 (cfg 1: factor + solve of one
+    // system 39 -> 19 ms, schedule built in 0.2 s).
     int split;
-    if (mode == PM_FACTOR)
-        split = (sd.lay.n_lu >= 4000000 || batch_cols >= 2048) ? 0 : 2;
-    else
+    if (mode == PM_FACTOR) {
+        if (batch_cols >= 2048) split = 0;
+        else split = sd.info_mac >= 4000000 ? 3 : 2;
+    } else {
         split = batch_cols >= 4096 ? 3 : 2;
+    }
     if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_SPLIT")) split = std::atoi(e);
     auto key = std::make_pair(mode, split);
     auto it = sd.level.find(key);
@@ -742,26 +747,76 @@ DEF_SWS(klujax_cuda_solve_with_symbol_c128, 1, 0)
 DEF_SWS(klujax_cuda_tsolve_with_symbol_f64, 0, 1)
 DEF_SWS(klujax_cuda_tsolve_with_symbol_c128, 1, 1)
 
+// One-shot `solve` (klujax.cpp:251-380: analyze + factor + solve + free, every call).  The
+// analysis, the pivoting seed factorization and the schedule only depend on the pattern, so the
+// last few patterns keep their symbolic object (with the device copies of (Ai, Aj) and of the
+// schedule): a caller looping over `solve` with one pattern pays them once.  Eviction frees the
+// object like klujax.cpp:336 does after every call.
+namespace {
+struct SolveCacheEntry {
+    int n = 0;
+    std::vector<int32_t> Ai, Aj;
+    uint64_t sym = 0;
+    DevBuf dAi, dAj;
+    uint64_t stamp = 0;
+};
+std::mutex g_solve_cache_mu;
+std::vector<std::unique_ptr<SolveCacheEntry>> g_solve_cache;
+uint64_t g_solve_stamp = 0;
+constexpr size_t kSolveCacheEntries = 4;
+}  // namespace
+
 static int do_solve(int cx, int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai_host,
                     const int32_t* Aj_host, const double* Ax, const double* b, double* x,
                     int32_t* status, double* growth, void* stream) {
-    uint64_t sym = 0;
-    int rc = klujax_cuda_analyze(n_col, n_nz, Ai_host, Aj_host, &sym);
-    if (rc) return rc;
-    DevBuf dAi, dAj;
+    if (n_nz < 0 || (n_nz > 0 && (!Ai_host || !Aj_host))) return fail(KLU_INVALID, "solve: null indices");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = dAi.alloc(sizeof(int) * (n_nz + 1));
-    if (e == cudaSuccess) e = dAj.alloc(sizeof(int) * (n_nz + 1));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dAi.p, Ai_host, sizeof(int) * n_nz, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dAj.p, Aj_host, sizeof(int) * n_nz, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) {
-        klujax_cuda_free_symbolic(sym, nullptr);
-        return fail(KLU_OUT_OF_MEMORY, cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lock(g_solve_cache_mu);
+    SolveCacheEntry* hit = nullptr;
+    for (auto& e : g_solve_cache)
+        if (e->n == n_col && static_cast<int>(e->Ai.size()) == n_nz &&
+            std::equal(e->Ai.begin(), e->Ai.end(), Ai_host) && std::equal(e->Aj.begin(), e->Aj.end(), Aj_host)) {
+            hit = e.get();
+            break;
+        }
+    if (!hit) {
+        auto ne = std::make_unique<SolveCacheEntry>();
+        int rc = klujax_cuda_analyze(n_col, n_nz, Ai_host, Aj_host, &ne->sym);
+        if (rc) return rc;
+        ne->n = n_col;
+        ne->Ai.assign(Ai_host, Ai_host + n_nz);
+        ne->Aj.assign(Aj_host, Aj_host + n_nz);
+        cudaError_t e = ne->dAi.alloc(sizeof(int) * (n_nz + 1));
+        if (e == cudaSuccess) e = ne->dAj.alloc(sizeof(int) * (n_nz + 1));
+        if (e == cudaSuccess) e = cudaMemcpy(ne->dAi.p, Ai_host, sizeof(int) * n_nz, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(ne->dAj.p, Aj_host, sizeof(int) * n_nz, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            klujax_cuda_free_symbolic(ne->sym, nullptr);
+            return fail(KLU_OUT_OF_MEMORY, cudaGetErrorString(e));
+        }
+        if (g_solve_cache.size() >= kSolveCacheEntries) {  // evict the least recently used pattern
+            size_t victim = 0;
+            for (size_t i = 1; i < g_solve_cache.size(); ++i)
+                if (g_solve_cache[i]->stamp < g_solve_cache[victim]->stamp) victim = i;
+            cudaDeviceSynchronize();  // its kernels may still be in flight on another stream
+            klujax_cuda_free_symbolic(g_solve_cache[victim]->sym, nullptr);
+            g_solve_cache.erase(g_solve_cache.begin() + victim);
+        }
+        g_solve_cache.push_back(std::move(ne));
+        hit = g_solve_cache.back().get();
     }
-    rc = do_solve_with_symbol(cx, 0, sym, n_lhs, n_col, n_rhs, n_nz, dAi.as<int32_t>(),
-                              dAj.as<int32_t>(), Ax, b, x, status, growth, stream);
-    cudaStreamSynchronize(st);  // the symbolic object dies with this call, like klujax.cpp:336
-    klujax_cuda_free_symbolic(sym, nullptr);
+    hit->stamp = ++g_solve_stamp;
+    int rc = do_solve_with_symbol(cx, 0, hit->sym, n_lhs, n_col, n_rhs, n_nz, hit->dAi.as<int32_t>(),
+                                  hit->dAj.as<int32_t>(), Ax, b, x, status, growth, stream);
+    if (rc) {  // a failed call (singular seed, ...) leaves nothing behind, like the reference
+        cudaStreamSynchronize(st);
+        for (size_t i = 0; i < g_solve_cache.size(); ++i)
+            if (g_solve_cache[i].get() == hit) {
+                klujax_cuda_free_symbolic(hit->sym, nullptr);
+                g_solve_cache.erase(g_solve_cache.begin() + i);
+                break;
+            }
+    }
     return rc;
 }
 int klujax_cuda_solve_f64(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai,
