@@ -161,7 +161,116 @@ struct LvArgs {
     const int* sysidx;
     int* bad;                       // [L] OR of singular pivots
     unsigned long long* growth2;    // [L] max |L|^2 as ordered bits
+    int gsz;                        // cooperative kernels: CTAs that share one batch column
+    unsigned* bar;                  // cooperative kernels: [columns] arrival counters (zeroed per launch)
 };
+
+// ---- cooperative variants: several CTAs (SMs) per batch column --------------------------
+// With fewer batch columns than SMs (cfg 1: ONE system) a column gets gsz CTAs; the items of a
+// level are dealt over all their threads and the barrier between levels is an arrival counter
+// in global memory (the kernels are launched with cudaLaunchCooperativeKernel, so all CTAs
+// are resident).  Values written by another CTA are read with ld.global.cg (L2, never a
+// stale L1 line).
+__device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned nblk, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nblk;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (*reinterpret_cast<volatile unsigned*>(ctr) < target) __nanosleep(20);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) lv_factor_coop(const LvArgs a) {
+    using S = Sc<T>;
+    using V_t = typename S::V;
+    V_t* V = static_cast<V_t*>(a.V);
+    const int grp = blockIdx.x / a.gsz, rank = blockIdx.x % a.gsz;
+    const int m = grp;  // one system per group of CTAs
+    if (m >= a.L) return;
+    const long long sm = a.sysidx ? a.sysidx[m] : m;
+    unsigned target = 0;
+    unsigned* ctr = a.bar + grp;
+    const int stride = a.gsz * blockDim.x, first = rank * blockDim.x + threadIdx.x;
+    int te = __ldg(a.level_ptr);
+    for (int l = 0; l < a.nlevels; ++l) {
+        const int tb = te;
+        te = __ldg(a.level_ptr + l + 1);
+        for (int t = tb + first; t < te; t += stride) {
+            const int4 rec = __ldg(a.task + 2 * t), fp = __ldg(a.task + 2 * t + 1);
+            const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
+            const int2* pr = a.pair + rec.z;
+            V_t* o = V + (long long)rec.x * a.lpad + sm * a.vss;
+            const V_t o0 = __ldcg(o);
+            V_t acc = S::zero();
+            if (plen)
+                S::fma_acc(acc, __ldcg(V + (long long)fp.x * a.lpad + sm * a.vss),
+                           __ldcg(V + (long long)fp.y * a.lpad + sm * a.vss));
+#pragma unroll 4
+            for (int p = 0; p < plen - 1; ++p) {
+                const int2 ab = __ldg(pr + p);
+                S::fma_acc(acc, __ldcg(V + (long long)ab.x * a.lpad + sm * a.vss),
+                           __ldcg(V + (long long)ab.y * a.lpad + sm * a.vss));
+            }
+            V_t v = S::sub(o0, acc);
+            if (kind == TK_RECIP) {
+                if (S::bad_pivot(v)) a.bad[m] = 1;
+                v = S::recip(v);
+            } else if (kind >= TK_MUL) {
+                v = S::mul(v, __ldcg(V + (long long)rec.y * a.lpad + sm * a.vss));
+                if (kind == TK_MUL_TRACK)
+                    atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v)));
+            }
+            *o = v;
+        }
+        group_barrier(ctr, a.gsz, target);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) lv_solve_coop(const LvArgs a) {
+    using S = Sc<T>;
+    using V_t = typename S::V;
+    const V_t* V = static_cast<const V_t*>(a.V);
+    V_t* X = static_cast<V_t*>(a.X);
+    const int grp = blockIdx.x / a.gsz, rank = blockIdx.x % a.gsz;
+    const long long q = grp;  // one right-hand-side column per group of CTAs
+    if (q >= a.Q) return;
+    const int m = static_cast<int>(q / a.r);
+    const long long sm = a.sysidx ? a.sysidx[m] : m;
+    unsigned target = 0;
+    unsigned* ctr = a.bar + grp;
+    const int stride = a.gsz * blockDim.x, first = rank * blockDim.x + threadIdx.x;
+    int te = __ldg(a.level_ptr);
+    for (int l = 0; l < a.nlevels; ++l) {
+        const int tb = te;
+        te = __ldg(a.level_ptr + l + 1);
+        for (int t = tb + first; t < te; t += stride) {
+            const int4 rec = __ldg(a.task + 2 * t), fp = __ldg(a.task + 2 * t + 1);
+            const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
+            const int2* pr = a.pair + rec.z;
+            V_t* o = X + (long long)(rec.x - a.n_val) * a.xrs + q * a.xcs;
+            const V_t o0 = __ldcg(o);
+            V_t acc = S::zero();
+            if (plen)
+                S::fma_acc(acc, __ldg(V + (long long)fp.x * a.lpad + sm * a.vss),
+                           __ldcg(X + (long long)(fp.y - a.n_val) * a.xrs + q * a.xcs));
+#pragma unroll 4
+            for (int p = 0; p < plen - 1; ++p) {
+                const int2 ab = __ldg(pr + p);
+                S::fma_acc(acc, __ldg(V + (long long)ab.x * a.lpad + sm * a.vss),
+                           __ldcg(X + (long long)(ab.y - a.n_val) * a.xrs + q * a.xcs));
+            }
+            V_t v = S::sub(o0, acc);
+            if (kind >= TK_MUL) v = S::mul(v, __ldg(V + (long long)rec.y * a.lpad + sm * a.vss));
+            *o = v;
+        }
+        group_barrier(ctr, a.gsz, target);
+    }
+}
 
 // Refactorization: thread per (task, system) inside a level, CTA per slice of systems.
 template <typename T>
@@ -347,6 +456,25 @@ static int want_sysmajor(long long L, int num_sms) {
     return L <= num_sms;
 }
 
+// CTAs per batch column for the cooperative kernels: 0 = use the ordinary kernels.
+template <typename K>
+static int coop_group_size(K kernel, long long ncols, int slice, int num_sms, long long ntasks, int nlevels) {
+    if (const char* e = std::getenv("KLUJAX_CUDA_COOP"))
+        if (std::atoi(e) == 0) return 0;
+    if (slice != 1 || ncols * 2 > num_sms) return 0;
+    // the global-memory barrier costs ~1.6 us per level against ~0.5 us for __syncthreads():
+    // worth it only when an average level is wider than one CTA (cfg 1: the factorization
+    // 13.7 -> 7.8 ms, while its narrow solve levels would go 0.9 -> 2.0 ms)
+    if (ntasks < 1024LL * std::max(nlevels, 1)) return 0;
+    int dev = 0, coop = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 1024, 0) != cudaSuccess || occ < 1) return 0;
+    long long g = std::min<long long>(32, (static_cast<long long>(occ) * num_sms) / ncols);
+    if (const char* e = std::getenv("KLUJAX_CUDA_COOP_G")) g = std::min<long long>(g, std::max(1, std::atoi(e)));
+    return g >= 2 ? static_cast<int>(g) : 0;
+}
+
 // Threads per CTA of the level kernels: enough for the widest level of the slice, at most 1024.
 static int level_threads(int max_level_tasks, int slice) {
     if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_THREADS")) return std::max(32, std::min(1024, std::atoi(e)));
@@ -393,8 +521,10 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
         V = static_cast<V_t*>(tmpV);
         Rs = static_cast<double*>(tmpRs);
     }
-    // aux: barrier counters (2), bad[L], growth2[L]
-    const size_t aux_bytes = 64 + sizeof(int) * (size_t)c.L + sizeof(unsigned long long) * (size_t)c.L + 64;
+    // aux: bad[L], growth2[L], then the arrival counters of the cooperative kernels
+    const size_t ncnt = static_cast<size_t>(std::max<long long>(c.L, (long long)c.L * std::max(c.r, 1))) ;
+    const size_t aux_bytes = 64 + sizeof(int) * (size_t)c.L + sizeof(unsigned long long) * (size_t)c.L + 64 +
+                             (ncnt <= 1024 ? sizeof(unsigned) * ncnt : 0) + 64;
     if (!chk(cudaMallocAsync(&tmpAux, aux_bytes, c.st), "alloc aux") ||
         !chk(cudaMemsetAsync(tmpAux, 0, aux_bytes, c.st), "memset aux")) {
         cleanup();
@@ -402,6 +532,7 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
     }
     unsigned long long* growth2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(tmpAux) + 64);
     int* bad = reinterpret_cast<int*>(growth2 + c.L);
+    unsigned* coop_bar = ncnt <= 1024 ? reinterpret_cast<unsigned*>(bad + ((c.L + 15) / 16) * 16) : nullptr;
 
     const long long v_slot = sysmajor ? 1 : lpad, v_sys = sysmajor ? c.n_val : 1;
     const long long r_row = sysmajor ? 1 : lpad, r_sys = sysmajor ? c.n : 1;
@@ -422,7 +553,19 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
         a.V = V; a.X = nullptr; a.sysidx = c.sysidx; a.bad = bad; a.growth2 = growth2;
         a.slice = pick_slice(c.L, c.num_sms);
         const int grid = static_cast<int>(std::min<long long>((c.L + a.slice - 1) / a.slice, 2LL * c.num_sms));
-        lv_factor<T><<<grid, level_threads(pf->max_level_tasks, a.slice), 0, c.st>>>(a);
+        a.gsz = coop_bar ? coop_group_size(lv_factor_coop<T>, c.L, a.slice, c.num_sms, pf->ntasks, pf->nlevels) : 0;
+        if (a.gsz >= 2) {
+            a.bar = coop_bar;
+            void* kargs[] = {&a};
+            if (!chk(cudaMemsetAsync(coop_bar, 0, sizeof(unsigned) * c.L, c.st), "memset barrier") ||
+                !chk(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lv_factor_coop<T>), dim3(static_cast<unsigned>(c.L * a.gsz)),
+                                                 dim3(1024), kargs, 0, c.st), "cooperative factor")) {
+                cleanup();
+                return KLU_OUT_OF_MEMORY;
+            }
+        } else {
+            lv_factor<T><<<grid, level_threads(pf->max_level_tasks, a.slice), 0, c.st>>>(a);
+        }
         lv_finish_status<<<(c.L + 255) / 256, 256, 0, c.st>>>(c.L, bad, growth2, c.pattern_bad,
                                                             c.status, c.growth);
     }
@@ -447,7 +590,19 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
         a.V = V; a.X = X; a.sysidx = c.sysidx; a.bad = bad; a.growth2 = growth2;
         a.slice = xslice;
         const int grid = static_cast<int>(std::min<long long>((Q + a.slice - 1) / a.slice, 2LL * c.num_sms));
-        lv_solve<T><<<grid, level_threads(ps->max_level_tasks, a.slice), 0, c.st>>>(a);
+        a.gsz = coop_bar ? coop_group_size(lv_solve_coop<T>, Q, a.slice, c.num_sms, ps->ntasks, ps->nlevels) : 0;
+        if (a.gsz >= 2) {
+            a.bar = coop_bar;
+            void* kargs[] = {&a};
+            if (!chk(cudaMemsetAsync(coop_bar, 0, sizeof(unsigned) * Q, c.st), "memset barrier") ||
+                !chk(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lv_solve_coop<T>), dim3(static_cast<unsigned>(Q * a.gsz)),
+                                                 dim3(1024), kargs, 0, c.st), "cooperative solve")) {
+                cleanup();
+                return KLU_OUT_OF_MEMORY;
+            }
+        } else {
+            lv_solve<T><<<grid, level_threads(ps->max_level_tasks, a.slice), 0, c.st>>>(a);
+        }
         lv_store_x<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
             c.L, c.n, c.r, static_cast<V_t*>(c.x), tr ? c.pnum : c.q, tr ? 1 : 0, Rs, r_row, r_sys, c.sysidx, X,
             x_row, x_col);
