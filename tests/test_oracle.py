@@ -207,3 +207,20 @@ def test_triangular_all_singleton_blocks(oracle, dtype):
         A = dense(Ai, Aj, Ax[m], n)
         assert relerr(x[m], np.linalg.solve(A, b[m])) < 1e-12
         assert relerr(xt[m], np.linalg.solve(A.T, b[m])) < 1e-12
+
+
+def test_cfg1_cpu_latency_reference(oracle, capsys):
+    """Config 1 on the CPU side (the figure DESIGN.md quotes next to tools/time_cfg1.py): the
+    restated KLU's analyze + factor + solve of the n = 1000 system; checked against LAPACK."""
+    import time
+    from klujax_b200 import synth
+    Ai, Aj, Ax = synth.random_dd()
+    n = 1000
+    b = np.random.default_rng(1).standard_normal((1, n, 1))
+    t0 = time.perf_counter()
+    x = oracle.solve(Ai, Aj, Ax, b)
+    dt = time.perf_counter() - t0
+    A = synth.dense_from_coo(Ai, Aj, Ax[0], n)
+    assert np.linalg.norm(A @ x[0] - b[0]) / np.linalg.norm(b[0]) < 1e-12
+    with capsys.disabled():
+        print(f"\n[cfg1 CPU] analyze + factor + solve, one thread: {dt * 1e3:.1f} ms")
