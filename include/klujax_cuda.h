@@ -174,6 +174,23 @@ int klujax_cuda_symbolic_perm(uint64_t symbolic, int32_t* P, int32_t* Q, int32_t
 int klujax_cuda_symbolic_pattern(uint64_t symbolic, int is_complex, int32_t* Pnum, int32_t* Lp,
                                  int32_t* Li, int32_t* Up, int32_t* Ui);
 
+/* ---- register-resident regime: planner self-test (host only, TEST INFRASTRUCTURE) ----------
+ * Builds the register-resident program of the fused factor + solve (klujax.cpp:431-451) for a
+ * seeded symbolic handle and runs it on the planner's HOST INTERPRETER for ONE system: the
+ * parity tests check the schedule against the oracle without a GPU.  No operator above ever
+ * calls this; the product path is the generated sm_100a kernel and has no CPU fallback.
+ *   Ax_host: values in the COO order of the analyze call; b_host, x_host: [n_col, n_rhs]
+ *   stats[16]: 0 value registers, 1 multiply-add instructions, 2 useful multiply-adds,
+ *     3 shuffle broadcasts, 4 pivots, 5 multiplier instructions, 6 zero-fill instructions,
+ *     7 parking stores, 8 parked-row multiply-adds, 9 planes of parked values, 10 epochs,
+ *     11 rows kept in registers, 12 load instructions, 13 instructions in total,
+ *     14 16-bit tables, 15 shared memory per warp (bytes)
+ *   ptx_path: if not NULL the generated PTX is written there (tests assemble it with ptxas) */
+int klujax_cuda_rowreg_selftest(uint64_t symbolic, int is_complex, int transpose, int n_rhs,
+                                const double* Ax_host, const double* b_host, double* x_host,
+                                int32_t* status_out, double* growth_out, int64_t* stats16,
+                                const char* ptx_path);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,9 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 OUT = os.path.join(OUT_DIR, "libklujax_cuda.so")
-SOURCES = ["klujax_cuda.cu", "ordering.cpp", "seed_lu.cpp", "plan.cpp"]
-HEADERS = ["symbolic.hpp", "plan.hpp", "kernels_small.cuh", "kernels_level.cuh",
-           os.path.join("..", "..", "include", "klujax_cuda.h")]
+SOURCES = ["klujax_cuda.cu", "ordering.cpp", "seed_lu.cpp", "plan.cpp", "rowreg.cpp", "rowreg_ptx.cpp"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".hpp", ".cuh", ".h"))) + \
+          [os.path.join("..", "..", "include", "klujax_cuda.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-shared", "--expt-relaxed-constexpr"]

@@ -19,6 +19,7 @@
 
 #include "../../include/klujax_cuda.h"
 #include "plan.hpp"
+#include "rowreg.hpp"
 #include "symbolic.hpp"
 #include "kernels_small.cuh"
 #include "kernels_level.cuh"
@@ -76,6 +77,22 @@ struct SmallProg {
 };
 
 // Everything that depends on the pivot sequence (one per value type).
+// A generated register-resident kernel (rowreg.hpp): plan, PTX assembled by the driver's JIT,
+// the 16-bit tables on the device.  One per (transpose, right-hand-side width).
+struct RRKernel {
+    bool usable = false;
+    std::string why;
+    rr::Plan plan;
+    rr::PtxKernel pk;
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kern = nullptr;
+    DevBuf tabs, splace;  // splace: slot of every entry of the (col,row)-sorted pattern (COO map of the call)
+    int regs = 0, ctas_per_sm = 1;
+    ~RRKernel() {
+        if (lib) cudaLibraryUnload(lib);
+    }
+};
+
 struct Seeded {
     bool ok = false;
     PivotPlan piv;
@@ -84,6 +101,8 @@ struct Seeded {
     DevBuf d_colptr, d_srow, d_sslot, d_rs_ptr, d_rs_slot, d_pnum, d_q;
     std::map<std::pair<int, int>, std::unique_ptr<SmallProg>> small;  // key (mode, rc + 1000 * wide)
     std::map<std::pair<int, int>, std::unique_ptr<LevelProg>> level;
+    std::map<std::pair<int, int>, std::unique_ptr<RRKernel>> rowreg;  // key (transpose, n_rhs)
+    DevBuf d_scsc;  // CSC position of every entry of the (col,row)-sorted pattern (COO map of the rowreg kernels)
     int64_t info_levels = 0, info_mac = 0, info_nbatch = 0, info_stream_words = 0;
 };
 
@@ -95,7 +114,7 @@ struct Symbolic {
     // per-stream scratch of the COO map (slot of every COO entry of the call + pattern flag):
     // calls on different streams may overlap on the device
     struct Scratch {
-        DevBuf coo_dst, bad;
+        DevBuf coo_dst, coo_csc, bad;
     };
     std::map<cudaStream_t, std::unique_ptr<Scratch>> scratch;
     Scratch* cur = nullptr;  // scratch of the call in flight (under mu)
@@ -180,6 +199,11 @@ static int upload_seeded(Symbolic* S, int cx) {
     CUDA_OK(sd.d_colptr.upload(sd.lay.sorted_colptr));
     CUDA_OK(sd.d_srow.upload(sd.lay.sorted_row));
     CUDA_OK(sd.d_sslot.upload(sd.lay.sorted_slot));
+    {
+        std::vector<int> scsc(sd.lay.sorted_slot.size());
+        for (size_t q = 0; q < scsc.size(); ++q) scsc[q] = sd.lay.slot_csc[sd.lay.sorted_slot[q]];
+        CUDA_OK(sd.d_scsc.upload(scsc));
+    }
     CUDA_OK(sd.d_rs_ptr.upload(sd.lay.rs_ptr));
     CUDA_OK(sd.d_rs_slot.upload(sd.lay.rs_slot));
     CUDA_OK(sd.d_pnum.upload(sd.piv.Pnum));
@@ -460,6 +484,152 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// register-resident regime (rowreg.hpp): plan, generate PTX, JIT, launch
+// ---------------------------------------------------------------------------
+static bool rowreg_enabled() {
+    const char* e = std::getenv("KLUJAX_CUDA_ROWREG");  // read per call: tests switch it
+    return e ? std::atoi(e) != 0 : true;
+}
+
+static RRKernel* get_rowreg(Symbolic* S, int cx, bool transpose, int r) {
+    Seeded& sd = S->seeded[cx];
+    auto key = std::make_pair(transpose ? 1 : 0, r);
+    auto it = sd.rowreg.find(key);
+    if (it != sd.rowreg.end()) return it->second.get();
+    auto k = std::make_unique<RRKernel>();
+    RRKernel* K = k.get();
+    sd.rowreg.emplace(key, std::move(k));
+    rr::Options opt;
+    opt.r = r;
+    opt.transpose = transpose;
+    opt.max_regs = cx ? 60 : 120;  // beyond this the assembler spills too much (cfg 5 needs 58)
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_PINNED")) opt.pinned_rows = std::atoi(e);
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_MAXREGS")) opt.max_regs = std::atoi(e);
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_REBALANCE")) opt.rebalance = std::atoi(e) != 0;
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_LEVEL_ORDER")) opt.level_order = std::atoi(e) != 0;
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_STRIPE")) opt.stripe = std::atoi(e) != 0;
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_STRIPE_MIN")) opt.stripe_min = std::atoi(e);
+    if (!rr::build_plan(S->A, S->ord, sd.piv, sd.lay, cx != 0, opt, K->plan)) {
+        K->why = K->plan.why;
+        return K;
+    }
+    // warps per CTA: as many systems as shared memory holds, at most 8 (255 registers per thread)
+    {
+        rr::PtxKernel probe;
+        rr::emit_ptx(K->plan, probe);
+        const size_t per_warp = std::max<size_t>(probe.smem_per_warp, 1);
+        int wpc = static_cast<int>(std::min<size_t>(8, kMaxDynSmem / per_warp));
+        if (const char* e = std::getenv("KLUJAX_CUDA_RR_WPC")) wpc = std::max(1, std::min(wpc, std::atoi(e)));
+        if (wpc < 1) {
+            K->why = "shared memory of one system exceeds the CTA limit";
+            return K;
+        }
+        K->pk.warps_per_cta = wpc;
+    }
+    if (!rr::emit_ptx(K->plan, K->pk)) {
+        K->why = "PTX rendering failed";
+        return K;
+    }
+    if (const char* dump = std::getenv("KLUJAX_CUDA_RR_DUMP_PTX")) {
+        if (FILE* f = std::fopen(dump, "w")) {
+            std::fwrite(K->pk.ptx.data(), 1, K->pk.ptx.size(), f);
+            std::fclose(f);
+        }
+    }
+    std::vector<char> elog(16384, 0);
+    cudaJitOption jopt[2] = {cudaJitErrorLogBuffer, cudaJitErrorLogBufferSizeBytes};
+    void* jval[2] = {elog.data(), reinterpret_cast<void*>(static_cast<uintptr_t>(elog.size()))};
+    cudaError_t e = cudaLibraryLoadData(&K->lib, K->pk.ptx.c_str(), jopt, jval, 2, nullptr, nullptr, 0);
+    if (e != cudaSuccess) {
+        K->why = std::string("JIT of the generated PTX failed: ") + cudaGetErrorString(e) + " " + elog.data();
+        cudaGetLastError();
+        K->lib = nullptr;
+        return K;
+    }
+    e = cudaLibraryGetKernel(&K->kern, K->lib, K->pk.name.c_str());
+    if (e != cudaSuccess) {
+        K->why = std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return K;
+    }
+    const size_t smem = K->pk.smem_per_warp * K->pk.warps_per_cta;
+    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(K->kern), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem));
+    cudaFuncAttributes fa{};
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(K->kern));
+    int occ = 0;
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(K->kern),
+                                                          32 * K->pk.warps_per_cta, smem);
+    if (e != cudaSuccess || occ < 1) {
+        K->why = std::string("generated kernel cannot be launched: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return K;
+    }
+    K->regs = fa.numRegs;
+    K->ctas_per_sm = occ;
+    {
+        std::vector<int> sp(sd.lay.sorted_slot.size());
+        for (size_t q = 0; q < sp.size(); ++q) sp[q] = K->plan.place[sd.lay.slot_csc[sd.lay.sorted_slot[q]]];
+        if (K->splace.upload(sp) != cudaSuccess) {
+            K->why = "out of device memory for the slot map";
+            return K;
+        }
+    }
+    if (K->tabs.upload(K->plan.tabs) != cudaSuccess) {
+        K->why = "out of device memory for the tables";
+        return K;
+    }
+    if (std::getenv("KLUJAX_CUDA_RR_VERBOSE"))
+        std::fprintf(stderr, "[rowreg] n=%d r=%d: %d value registers, %d registers/thread, %zu B local, %d warps/CTA x %d CTA/SM, %zu B smem/warp, %zu instructions\n",
+                     K->plan.n, r, K->plan.P, fa.numRegs, fa.localSizeBytes, K->pk.warps_per_cta, occ,
+                     K->pk.smem_per_warp, K->plan.ins.size());
+    K->usable = true;
+    return K;
+}
+
+static int launch_rowreg(Symbolic* S, int cx, RRKernel* K, const Op& op) {
+    Seeded& sd = S->seeded[cx];
+    const int nz = op.nz;
+    coo_map_kernel<<<(nz + 255) / 256, 256, 0, op.st>>>(nz, sd.lay.n, op.Ai, op.Aj, sd.d_colptr.as<int>(),
+                                                       sd.d_srow.as<int>(), K->splace.as<int>(),
+                                                       S->cur->coo_csc.as<int>(), S->cur->bad.as<int>());
+    CUDA_OK(cudaGetLastError());
+    const void* Ax = op.Ax;
+    const void* b = op.b;
+    void* x = op.x;
+    const void* tabs = K->tabs.p;
+    const void* dst = S->cur->coo_csc.p;
+    void* status = op.status;
+    void* growth = op.growth;
+    const void* bad = S->cur->bad.p;
+    unsigned long long axs = static_cast<unsigned long long>(op.ax_stride), bs = static_cast<unsigned long long>(op.b_stride);
+    unsigned int L = static_cast<unsigned int>(op.L);
+    static const bool do_prof = std::getenv("KLUJAX_CUDA_PROFILE") != nullptr;
+    unsigned long long* dprof = nullptr;
+    if (do_prof) {
+        cudaMalloc(reinterpret_cast<void**>(&dprof), 64);
+        cudaMemset(dprof, 0, 64);
+    }
+    void* args[] = {&Ax, &b, &x, &tabs, &dst, &status, &growth, &bad, &axs, &bs, &dprof, &L};
+    const int wpc = K->pk.warps_per_cta;
+    const long long ctas = (static_cast<long long>(op.L) + wpc - 1) / wpc;
+    const int grid = static_cast<int>(std::min<long long>(ctas, static_cast<long long>(K->ctas_per_sm) * num_sms()));
+    CUDA_OK(cudaLaunchKernel(reinterpret_cast<const void*>(K->kern), dim3(grid), dim3(32 * wpc), args,
+                             K->pk.smem_per_warp * wpc, op.st));
+    if (do_prof) {
+        unsigned long long h[8];
+        cudaStreamSynchronize(op.st);
+        cudaMemcpy(h, dprof, 64, cudaMemcpyDeviceToHost);
+        cudaFree(dprof);
+        const double ns = h[4] ? static_cast<double>(h[4]) : 1.0;
+        std::fprintf(stderr, "[PHASES rowreg] L=%d grid=%d x %d warps: cycles/system: stage %.0f | scale+load %.0f | eliminate %.0f | back-solve+store %.0f\n",
+                     op.L, grid, wpc, h[0] / ns, h[1] / ns, h[2] / ns, h[3] / ns);
+    }
+    return 0;
+}
+
 static int run_numeric(Symbolic* S, int cx, const Op& op) {
     std::lock_guard<std::mutex> lock(S->mu);
     Seeded& sd = S->seeded[cx];
@@ -470,6 +640,7 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
         if (!slot) {
             slot = std::make_unique<Symbolic::Scratch>();
             CUDA_OK(slot->coo_dst.alloc(sizeof(int) * (S->A.rowidx.size() + 1)));
+            CUDA_OK(slot->coo_csc.alloc(sizeof(int) * (S->A.rowidx.size() + 1)));
             CUDA_OK(slot->bad.alloc(sizeof(int)));
             CUDA_OK(cudaMemset(slot->bad.p, 0, sizeof(int)));
         }
@@ -486,6 +657,13 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
         CUDA_OK(cudaGetLastError());
     } else if (!sd.ok) {
         return fail(KLU_INVALID, "numeric handle without a factorization");
+    }
+    if (sd.regime == 0 && op.mode == PM_FACTOR_SOLVE && !op.store_numeric && op.r >= 1 && op.r <= 4 &&
+        op.status && op.growth && rowreg_enabled()) {
+        // fused factor + solve that keeps nothing: the register-resident kernel, if the pattern fits
+        RRKernel* K = get_rowreg(S, cx, false, op.r);
+        if (K->usable) return launch_rowreg(S, cx, K, op);
+        if (std::getenv("KLUJAX_CUDA_ROWREG_REQUIRE")) return fail(KLU_TOO_LARGE, "register-resident kernel unavailable: " + K->why);
     }
     if (sd.regime == 0) return cx ? launch_small<zc>(S, 1, op) : launch_small<double>(S, 0, op);
     // level-scheduled regime
@@ -705,6 +883,66 @@ int klujax_cuda_symbolic_pattern(uint64_t symbolic, int is_complex, int32_t* Pnu
     }
     if (Up) Up[n] = up;
     if (Lp) Lp[n] = lp;
+    return 0;
+}
+
+int klujax_cuda_rowreg_selftest(uint64_t symbolic, int is_complex, int transpose, int n_rhs,
+                                const double* Ax_host, const double* b_host, double* x_host,
+                                int32_t* status_out, double* growth_out, int64_t* stats16,
+                                const char* ptx_path) {
+    Symbolic* S = sym_of(symbolic);
+    if (!S) return fail(KLU_INVALID, "rowreg_selftest: null handle");
+    const int cx = is_complex ? 1 : 0;
+    const Seeded& sd = S->seeded[cx];
+    if (!sd.ok) return fail(KLU_INVALID, "rowreg_selftest: not seeded");
+    rr::Options opt;
+    opt.r = n_rhs;
+    opt.transpose = transpose != 0;
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_PINNED")) opt.pinned_rows = std::atoi(e);
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_MAXREGS")) opt.max_regs = std::atoi(e);
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_REBALANCE")) opt.rebalance = std::atoi(e) != 0;
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_LEVEL_ORDER")) opt.level_order = std::atoi(e) != 0;
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_STRIPE")) opt.stripe = std::atoi(e) != 0;
+    if (const char* e = std::getenv("KLUJAX_CUDA_RR_STRIPE_MIN")) opt.stripe_min = std::atoi(e);
+    rr::Plan plan;
+    const bool ok = rr::build_plan(S->A, S->ord, sd.piv, sd.lay, cx != 0, opt, plan);
+    rr::PtxKernel pk;
+    if (ok) rr::emit_ptx(plan, pk);
+    if (stats16) {
+        const rr::Stats& st = plan.st;
+        const int64_t v[16] = {st.P, st.mac_ins, st.useful_mac, st.bcast, st.pivots, st.lmul, st.zero, st.dump,
+                               st.mac_s, st.planes, st.epochs, st.pinned, st.loadv,
+                               static_cast<int64_t>(plan.ins.size()), static_cast<int64_t>(plan.tabs.size() / 32),
+                               static_cast<int64_t>(pk.smem_per_warp)};
+        std::copy(v, v + 16, stats16);
+    }
+    if (!ok) return fail(KLU_TOO_LARGE, "rowreg plan: " + plan.why);
+    if (ptx_path) {
+        FILE* f = std::fopen(ptx_path, "w");
+        if (!f) return fail(KLU_INVALID, "rowreg_selftest: cannot write the PTX file");
+        std::fwrite(pk.ptx.data(), 1, pk.ptx.size(), f);
+        std::fclose(f);
+    }
+    if (Ax_host && b_host && x_host) {
+        const int nz = static_cast<int>(S->A.rowidx.size()), n = sd.lay.n;
+        // analyze-call COO order -> analysed CSC order
+        int st = 0;
+        double g = 0.0;
+        if (cx) {
+            using Z = std::complex<double>;
+            const Z* ax = reinterpret_cast<const Z*>(Ax_host);
+            std::vector<Z> csc(nz);
+            for (int p = 0; p < nz; ++p) csc[p] = ax[S->A.coo_of[p]];
+            st = rr::emulate<Z>(plan, csc.data(), reinterpret_cast<const Z*>(b_host), reinterpret_cast<Z*>(x_host), &g);
+        } else {
+            std::vector<double> csc(nz);
+            for (int p = 0; p < nz; ++p) csc[p] = Ax_host[S->A.coo_of[p]];
+            st = rr::emulate<double>(plan, csc.data(), b_host, x_host, &g);
+        }
+        (void)n;
+        if (status_out) *status_out = st;
+        if (growth_out) *growth_out = g;
+    }
     return 0;
 }
 
