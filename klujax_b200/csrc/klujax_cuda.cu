@@ -487,9 +487,13 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
 // ---------------------------------------------------------------------------
 // register-resident regime (rowreg.hpp): plan, generate PTX, JIT, launch
 // ---------------------------------------------------------------------------
+// Opt-in (KLUJAX_CUDA_ROWREG=1): measured on B200 the generated straight-line kernels are bound by
+// instruction fetch (cfg 5: ~32 000 SASS instructions = 0.5 MB per system, ncu: 44 % of the stall
+// samples are "no instruction", IPC 0.25 per sub-partition) and lose to the shared-memory
+// interpreters (7.4 vs 5.0 ms), see profiles/rowreg_r02.md.
 static bool rowreg_enabled() {
     const char* e = std::getenv("KLUJAX_CUDA_ROWREG");  // read per call: tests switch it
-    return e ? std::atoi(e) != 0 : true;
+    return e ? std::atoi(e) != 0 : false;
 }
 
 static RRKernel* get_rowreg(Symbolic* S, int cx, bool transpose, int r) {
@@ -526,6 +530,7 @@ static RRKernel* get_rowreg(Symbolic* S, int cx, bool transpose, int r) {
             return K;
         }
         K->pk.warps_per_cta = wpc;
+        if (const char* e = std::getenv("KLUJAX_CUDA_RR_LOCKSTEP")) K->pk.lockstep = std::atoi(e) != 0;
     }
     if (!rr::emit_ptx(K->plan, K->pk)) {
         K->why = "PTX rendering failed";

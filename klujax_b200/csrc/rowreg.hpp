@@ -115,6 +115,7 @@ int emulate(const Plan& p, const T* Ax_csc, const T* b, T* x, double* growth);
 struct PtxKernel {
     std::string ptx, name;
     int warps_per_cta = 8;
+    bool lockstep = true;  // CTA barrier at every pivot: the warps share the instruction stream
     size_t smem_per_warp = 0;
     int P = 0;
 };

@@ -12,6 +12,8 @@
 //   ax_stride, b_stride (elements), L.
 #include <cstdarg>
 #include <cstdio>
+#include <string>
+#include <vector>
 
 #include "rowreg.hpp"
 
@@ -56,7 +58,6 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
     out.name = "klujax_rowreg";
 
     W body;
-    int nlab = 0;
     // helpers ---------------------------------------------------------------------------------
     auto tabload = [&](const char* dst, int tab) {  // u16 table entry of this lane -> u32 dst
         body("ld.global.nc.u16 %%h0, [%%tabl+%d];", tab * kLanes * 2);
@@ -77,6 +78,9 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
         body("mov.b64 %s, {%%s2, %%s3};", dst);
     };
     char rx[32], ry[32], a1[48], a2[48], a3[48], a4[48];
+    const bool lockstep = out.lockstep;
+    std::vector<std::string> lz_keys;  // masked multipliers of the current pivot: "reg:Ltemp:mask"
+    int lz_base = 0;
     auto RX = [&](int q) { snprintf(rx, sizeof rx, "%%rx%d", q); return rx; };
     auto RY = [&](int q) { snprintf(ry, sizeof ry, "%%ry%d", q); return ry; };
 
@@ -227,38 +231,28 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
                 break;
             }
             case OP_PIVOT: {
-                const int L0 = nlab++;
+                lz_base += static_cast<int>(lz_keys.size());
+                lz_keys.clear();
+                // The code is one long straight line (hundreds of KB): the warps of the CTA walk it
+                // together, so that an instruction line fetched by one is in the instruction cache for
+                // the others (ncu: 44 % of the stall samples were "no instruction" without this).
+                if (lockstep) body("bar.sync 0;");
                 body("// ---- pivot (register %d, lane %d)", in.a, in.b);
                 shfl64("%dx", RX(in.a), in.b);
                 if (cx) {
+                    // 1/d = conj(d) / |d|^2.  Rows are scaled to max |a| = 1, so |d|^2 leaves the range
+                    // of a double only for a pivot that is numerically zero (or after overflow):
+                    // both are reported as KLU_SINGULAR.
                     shfl64("%dy", RY(in.a), in.b);
                     body("mul.f64 %%fm, %%dx, %%dx;");
                     body("fma.rn.f64 %%fm, %%dy, %%dy, %%fm;");
                     body("setp.gt.f64 %%p1, %%fm, 0d05E0000000000000;");           // ~1e-280
                     body("setp.lt.and.f64 %%p1, %%fm, 0d7A10000000000000, %%p1;");  // ~1e280
-                    body("@!%%p1 bra.uni SLOW%d;", L0);
+                    body("@!%%p1 mov.u32 %%bad, 1;");
                     body("rcp.rn.f64 %%fic, %%fm;");
                     body("mul.f64 %%ix%d, %%dx, %%fic;", in.t);
                     body("neg.f64 %%fic, %%fic;");
                     body("mul.f64 %%iy%d, %%dy, %%fic;", in.t);
-                    body("bra.uni DONE%d;", L0);
-                    body("SLOW%d:", L0);
-                    // scaled form; a zero or non-finite pivot raises the singular flag
-                    body("abs.f64 %%fa, %%dx;");
-                    body("abs.f64 %%fb, %%dy;");
-                    body("max.f64 %%fc, %%fa, %%fb;");
-                    body("setp.gt.f64 %%p1, %%fc, 0d0000000000000000;");
-                    body("setp.lt.and.f64 %%p1, %%fc, 0d7FF0000000000000, %%p1;");
-                    body("@!%%p1 mov.u32 %%bad, 1;");
-                    body("div.rn.f64 %%fa, %%dx, %%fc;");
-                    body("div.rn.f64 %%fb, %%dy, %%fc;");
-                    body("mul.f64 %%fm, %%fa, %%fa;");
-                    body("fma.rn.f64 %%fm, %%fb, %%fb, %%fm;");
-                    body("mul.f64 %%fm, %%fm, %%fc;");
-                    body("div.rn.f64 %%ix%d, %%fa, %%fm;", in.t);
-                    body("neg.f64 %%fb, %%fb;");
-                    body("div.rn.f64 %%iy%d, %%fb, %%fm;", in.t);
-                    body("DONE%d:", L0);
                 } else {
                     body("abs.f64 %%fa, %%dx;");
                     body("setp.gt.f64 %%p1, %%fa, 0d0000000000000000;");
@@ -326,23 +320,46 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
                 break;
             }
             case OP_MAC: {
-                maskpred("%p1", in.mask);
-                if (in.b >= 0) {
-                    snprintf(a3, sizeof a3, "%%rx%d", in.b);
-                    snprintf(a4, sizeof a4, "%%ry%d", in.b);
-                } else {
-                    snprintf(a3, sizeof a3, "%%lx%d", in.t2);
-                    snprintf(a4, sizeof a4, "%%ly%d", in.t2);
+                // Lanes outside the mask hold other entries in R[a]: they multiply by ZERO instead of
+                // being predicated off (the assembler turns a predicated FMA into FMA + two selects;
+                // a masked multiplier costs its selects once per pivot and mask, not per multiply-add).
+                char lkey[64];
+                snprintf(lkey, sizeof lkey, "%d:%d:%u", in.b, in.b >= 0 ? 0 : in.t2, in.mask);
+                int lz = -1;
+                for (size_t q = 0; q < lz_keys.size(); ++q)
+                    if (lz_keys[q] == lkey) lz = static_cast<int>(q);
+                if (lz < 0) {
+                    lz = static_cast<int>(lz_keys.size());
+                    lz_keys.push_back(lkey);
+                    if (in.b >= 0) {
+                        snprintf(a3, sizeof a3, "%%rx%d", in.b);
+                        snprintf(a4, sizeof a4, "%%ry%d", in.b);
+                    } else {
+                        snprintf(a3, sizeof a3, "%%lx%d", in.t2);
+                        snprintf(a4, sizeof a4, "%%ly%d", in.t2);
+                    }
+                    const int id = lz_base + lz;
+                    if (in.mask == 0xffffffffu) {
+                        body("neg.f64 %%mx%d, %s;", id, a3);
+                        if (cx) body("mov.f64 %%my%d, %s;", id, a4);
+                    } else {
+                        maskpred("%p1", in.mask);
+                        body("neg.f64 %%fa, %s;", a3);
+                        body("selp.f64 %%mx%d, %%fa, 0d0000000000000000, %%p1;", id);
+                        if (cx) body("selp.f64 %%my%d, %s, 0d0000000000000000, %%p1;", id, a4);
+                    }
                 }
-                body("neg.f64 %%fa, %s;", a3);
-                if (cx) {
-                    body("neg.f64 %%fb, %s;", a4);
-                    body("@%%p1 fma.rn.f64 %s, %%fa, %%ux%d, %s;", RX(in.a), in.t, RX(in.a));
-                    body("@%%p1 fma.rn.f64 %s, %s, %%uy%d, %s;", RX(in.a), a4, in.t, RX(in.a));
-                    body("@%%p1 fma.rn.f64 %s, %%fa, %%uy%d, %s;", RY(in.a), in.t, RY(in.a));
-                    body("@%%p1 fma.rn.f64 %s, %%fb, %%ux%d, %s;", RY(in.a), in.t, RY(in.a));
-                } else {
-                    body("@%%p1 fma.rn.f64 %s, %%fa, %%ux%d, %s;", RX(in.a), in.t, RX(in.a));
+                {
+                    const int id = lz_base + lz;  // mx = -l.x (masked), my = +l.y (masked)
+                    if (cx) {
+                        body("fma.rn.f64 %s, %%mx%d, %%ux%d, %s;", RX(in.a), id, in.t, RX(in.a));
+                        body("fma.rn.f64 %s, %%my%d, %%uy%d, %s;", RX(in.a), id, in.t, RX(in.a));
+                        body("fma.rn.f64 %s, %%mx%d, %%uy%d, %s;", RY(in.a), id, in.t, RY(in.a));
+                        body("neg.f64 %%fb, %%my%d;", id);
+                        body("fma.rn.f64 %s, %%fb, %%ux%d, %s;", RY(in.a), in.t, RY(in.a));
+                    } else {
+                        body("fma.rn.f64 %s, %%mx%d, %%ux%d, %s;", RX(in.a), id, in.t, RX(in.a));
+                    }
                 }
                 break;
             }
@@ -399,6 +416,8 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
                 break;
             }
             case OP_BCASTX: {
+                lz_base += static_cast<int>(lz_keys.size());  // back substitution: multipliers are U entries
+                lz_keys.clear();
                 snprintf(a1, sizeof a1, "%%ux%d", in.t2);
                 snprintf(a3, sizeof a3, "%%xx%d", in.t);
                 shfl64(a1, a3, in.b);
@@ -411,24 +430,26 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
             }
             case OP_MAC_S: {
                 maskpred("%p1", in.mask);
+                body("mov.f64 %%fc, 0d0000000000000000;");
                 if (cx) {
+                    body("mov.f64 %%fm, 0d0000000000000000;");
                     body("@%%p1 ld.shared.v2.f64 {%%fc, %%fm}, [%%sl+%d];", in.t2 * kLanes * VS);
                     body("neg.f64 %%fa, %%fc;");
                     body("neg.f64 %%fb, %%fm;");
-                    body("@%%p1 fma.rn.f64 %s, %%fa, %%ux%d, %s;", RX(in.a), in.t, RX(in.a));
-                    body("@%%p1 fma.rn.f64 %s, %%fm, %%uy%d, %s;", RX(in.a), in.t, RX(in.a));
-                    body("@%%p1 fma.rn.f64 %s, %%fa, %%uy%d, %s;", RY(in.a), in.t, RY(in.a));
-                    body("@%%p1 fma.rn.f64 %s, %%fb, %%ux%d, %s;", RY(in.a), in.t, RY(in.a));
+                    body("fma.rn.f64 %s, %%fa, %%ux%d, %s;", RX(in.a), in.t, RX(in.a));
+                    body("fma.rn.f64 %s, %%fm, %%uy%d, %s;", RX(in.a), in.t, RX(in.a));
+                    body("fma.rn.f64 %s, %%fa, %%uy%d, %s;", RY(in.a), in.t, RY(in.a));
+                    body("fma.rn.f64 %s, %%fb, %%ux%d, %s;", RY(in.a), in.t, RY(in.a));
                 } else {
                     body("@%%p1 ld.shared.f64 %%fc, [%%sl+%d];", in.t2 * kLanes * VS);
                     body("neg.f64 %%fa, %%fc;");
-                    body("@%%p1 fma.rn.f64 %s, %%fa, %%ux%d, %s;", RX(in.a), in.t, RX(in.a));
+                    body("fma.rn.f64 %s, %%fa, %%ux%d, %s;", RX(in.a), in.t, RX(in.a));
                 }
                 break;
             }
             case OP_STOREX: {
                 tabload("%t1", in.tab);
-                body("setp.ne.u32 %%p1, %%t1, 65535;");
+                body("setp.ne.and.u32 %%p1, %%t1, 65535, %%p3;");
                 body("mov.f64 %%fa, %s;", RX(in.a));
                 if (cx) body("mov.f64 %%fb, %s;", RY(in.a));
                 bool any = false;
@@ -486,6 +507,8 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
     k(".reg .f64 %%uy<%d>;", std::max(1, p.n_u));
     k(".reg .f64 %%xx<%d>;", std::max(1, p.n_x));
     k(".reg .f64 %%xy<%d>;", std::max(1, p.n_x));
+    k(".reg .f64 %%mx<%d>;", lz_base + static_cast<int>(lz_keys.size()) + 1);
+    k(".reg .f64 %%my<%d>;", lz_base + static_cast<int>(lz_keys.size()) + 1);
     k(".reg .f64 %%lx<%d>;", std::max(1, p.n_l));
     k(".reg .f64 %%ly<%d>;", std::max(1, p.n_l));
     k(".reg .f64 %%ix<%d>;", std::max(1, p.n_inv));
@@ -493,7 +516,7 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
     k(".reg .f64 %%fa, %%fb, %%fc, %%fm, %%fic, %%frs, %%dx, %%dy, %%gmax;");
     k(".reg .b32 %%s<4>;");
     k(".reg .u32 %%t<4>;");
-    k(".reg .u32 %%lane, %%warp, %%lanebit, %%sa, %%su, %%sl, %%sb, %%sx, %%srs, %%bad, %%m, %%L, %%mstep, %%e;");
+    k(".reg .u32 %%lane, %%warp, %%lanebit, %%sa, %%su, %%sl, %%sb, %%sx, %%srs, %%bad, %%m, %%meff, %%mbase, %%L, %%mstep, %%e;");
     k(".reg .s32 %%d0;");
     k(".reg .u16 %%h0;");
     k(".reg .pred %%p<4>;");
@@ -537,19 +560,24 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
     k("mad.lo.u32 %%m, %%t0, %d, %%warp;", WPC);
     k("mov.u32 %%t0, %%nctaid.x;");
     k("mul.lo.u32 %%mstep, %%t0, %d;", WPC);
-    k("setp.ge.u32 %%p0, %%m, %%L;");
+    k("mov.u32 %%t0, %%ctaid.x;");
+    k("mul.lo.u32 %%mbase, %%t0, %d;", WPC);  // first system of the CTA in this round (CTA-uniform)
+    k("setp.ge.u32 %%p0, %%mbase, %%L;");
     k("@%%p0 bra.uni EXIT;");
     k("SYSTEM:");
+    k("setp.lt.u32 %%p3, %%m, %%L;");          // p3: this warp has a system in this round
+    k("sub.u32 %%t0, %%L, 1;");
+    k("min.u32 %%meff, %%m, %%t0;");           // idle warps recompute the last system (no stores)
     // ---- stage the system: Abuf[dst[e]] = Ax[m][e], bbuf = b[m] ----
     k("mov.u64 %%ck0, %%clock64;");
     k("mov.u64 %%ck2, %%ck0;");
     k("mov.u64 %%ck3, %%ck0;");
-    k("mul.wide.u32 %%rd0, %%m, %d;", VS);
+    k("mul.wide.u32 %%rd0, %%meff, %d;", VS);
     k("mul.lo.u64 %%am, %%rd0, %%axs;");
     k("add.u64 %%am, %%am, %%Ax;");
     k("mul.lo.u64 %%bm, %%rd0, %%bs;");
     k("add.u64 %%bm, %%bm, %%b;");
-    k("mul.wide.u32 %%rd0, %%m, %d;", VS * n * r);
+    k("mul.wide.u32 %%rd0, %%meff, %d;", VS * n * r);
     k("add.u64 %%xm, %%x, %%rd0;");
     k("mov.u32 %%bad, 0;");
     k("mov.f64 %%gmax, 0d0000000000000000;");
@@ -604,7 +632,7 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
     k("ld.global.s32 %%d0, [%%pbad];");
     k("setp.ne.s32 %%p1, %%d0, 0;");
     k("@%%p1 mov.u32 %%bad, 0xfffffffd;");  // KLU_INVALID (-3)
-    k("setp.eq.u32 %%p1, %%lane, 0;");
+    k("setp.eq.and.u32 %%p1, %%lane, 0, %%p3;");
     k("mul.wide.u32 %%rd0, %%m, 4;");
     k("add.u64 %%rd0, %%rd0, %%status;");
     k("@%%p1 st.global.u32 [%%rd0], %%bad;");
@@ -616,6 +644,7 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
     k("mov.u64 %%ck4, %%clock64;");
     k("setp.ne.u64 %%p2, %%prof, 0;");
     k("setp.eq.and.u32 %%p2, %%lane, 0, %%p2;");
+    k("and.pred %%p2, %%p2, %%p3;");
     k("@!%%p2 bra.uni NOPROF;");
     k("cvta.to.global.u64 %%rd1, %%prof;");
     k("sub.u64 %%rd0, %%ck1, %%ck0;");
@@ -629,7 +658,8 @@ bool emit_ptx(const Plan& p, PtxKernel& out) {
     k("red.global.add.u64 [%%rd1+32], 1;");
     k("NOPROF:");
     k("add.u32 %%m, %%m, %%mstep;");
-    k("setp.lt.u32 %%p0, %%m, %%L;");
+    k("add.u32 %%mbase, %%mbase, %%mstep;");
+    k("setp.lt.u32 %%p0, %%mbase, %%L;");
     k("@%%p0 bra.uni SYSTEM;");
     k("EXIT:");
     k("ret;");
