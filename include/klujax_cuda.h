@@ -21,10 +21,14 @@
  *    argument errors detected on the host; klujax_cuda_last_error() has text.
  *  - Numerical failure is reported PER SYSTEM, on the device, KLU-style:
  *    status_dev[m] = 0 (KLU_OK), 1 (KLU_SINGULAR: zero or non-finite pivot),
+ *    2 (KLUJAX_CUDA_PIVOT_DRIFT: the pivot-parity certificate failed, see below),
  *    -3 (KLU_INVALID: index out of range / not in the analysed pattern);
- *    growth_dev[m] = max |L(i,k)| of system m (pivot-parity certificate: KLU's
- *    own threshold pivoting would have kept the static pivots while it stays
- *    <= 1/tol = 1000).  Either pointer may be NULL.  The reference collapses
+ *    growth_dev[m] = the certificate of system m: max |L(i,k)| over the columns
+ *    whose static pivot is the diagonal candidate, and for a column whose static
+ *    pivot is off-diagonal (KLU took the column maximum at seeding time)
+ *    max |L(i,k)| / tol and |L(diag,k)| / tol^2 - KLU's own threshold pivoting
+ *    (tol = 1e-3) would have chosen the same pivots while it stays <= 1/tol =
+ *    1000 (ties aside).  Either pointer may be NULL.  The reference collapses
  *    this into one ffi::Error for the whole batch (klujax.cpp:311-314); a
  *    binding reproduces that by raising if any status != 0.
  *  - Handles are opaque non-zero uint64 values, 0 = null, exactly like the
@@ -66,7 +70,8 @@ int klujax_cuda_solve_c128(int n_lhs, int n_col, int n_rhs, int n_nz, const int3
 /* ---- solve_with_symbol_* : klujax.cpp:382-509 ; tsolve_with_symbol_* : :511-636
  * Ai/Aj are DEVICE arrays here (they arrive as XLA buffers on every call and
  * may be ordered differently from the analyze call, klujax.py:319-321).
- * n_lhs_A / n_lhs_b may be 1 to broadcast against the other (klujax.py:1844-1848). */
+ * Ax is [n_lhs, n_nz] and b is [n_lhs, n_col, n_rhs] here; the _ex entry points below take a
+ * single matrix or a single right-hand side without materialising it (klujax.py:1844-1848). */
 int klujax_cuda_solve_with_symbol_f64(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz,
                                       const int32_t* Ai_dev, const int32_t* Aj_dev,
                                       const double* Ax_dev, const double* b_dev, double* x_dev,
@@ -84,6 +89,54 @@ int klujax_cuda_tsolve_with_symbol_c128(uint64_t symbolic, int n_lhs, int n_col,
                                         const double* Ax_dev, const double* b_dev, double* x_dev,
                                         int32_t* status_dev, double* growth_dev, void* stream);
 
+/* The entry points an XLA-FFI shim binds for solve_with_symbol / tsolve_with_symbol
+ * (INTEGRATION.md).  n_lhs_A and n_lhs_b are n_lhs or 1 (broadcast, stride 0 on the device).
+ * check = 0: enqueue only, per-system status and growth are left in the arrays.
+ * check != 0 reproduces the reference's semantics (klujax.cpp:311-314, :441): the stream is
+ * synchronised, systems whose pivot-parity certificate failed (status 2) or that met an exactly
+ * zero static pivot (status 1) are solved again on the GPU with a pivot sequence seeded from one
+ * of THEM, and the return value is 0 or the status of the first system that still fails
+ * (*first_bad_out = its index, *n_redone_out = systems solved again).  status 2 =
+ * KLUJAX_CUDA_PIVOT_DRIFT: KLU's threshold pivoting would not have kept the static pivots. */
+#define KLUJAX_CUDA_PIVOT_DRIFT 2
+int klujax_cuda_solve_with_symbol_ex_f64(uint64_t symbolic, int n_lhs, int n_lhs_A, int n_lhs_b,
+                                         int n_col, int n_rhs, int n_nz, const int32_t* Ai_dev,
+                                         const int32_t* Aj_dev, const double* Ax_dev,
+                                         const double* b_dev, double* x_dev, int32_t* status_dev,
+                                         double* growth_dev, int check, int32_t* first_bad_out,
+                                         int32_t* n_redone_out, void* stream);
+int klujax_cuda_solve_with_symbol_ex_c128(uint64_t symbolic, int n_lhs, int n_lhs_A, int n_lhs_b,
+                                          int n_col, int n_rhs, int n_nz, const int32_t* Ai_dev,
+                                          const int32_t* Aj_dev, const double* Ax_dev,
+                                          const double* b_dev, double* x_dev, int32_t* status_dev,
+                                          double* growth_dev, int check, int32_t* first_bad_out,
+                                          int32_t* n_redone_out, void* stream);
+int klujax_cuda_tsolve_with_symbol_ex_f64(uint64_t symbolic, int n_lhs, int n_lhs_A, int n_lhs_b,
+                                          int n_col, int n_rhs, int n_nz, const int32_t* Ai_dev,
+                                          const int32_t* Aj_dev, const double* Ax_dev,
+                                          const double* b_dev, double* x_dev, int32_t* status_dev,
+                                          double* growth_dev, int check, int32_t* first_bad_out,
+                                          int32_t* n_redone_out, void* stream);
+int klujax_cuda_tsolve_with_symbol_ex_c128(uint64_t symbolic, int n_lhs, int n_lhs_A, int n_lhs_b,
+                                           int n_col, int n_rhs, int n_nz, const int32_t* Ai_dev,
+                                           const int32_t* Aj_dev, const double* Ax_dev,
+                                           const double* b_dev, double* x_dev, int32_t* status_dev,
+                                           double* growth_dev, int check, int32_t* first_bad_out,
+                                           int32_t* n_redone_out, void* stream);
+
+/* The check + re-seed half of the _ex entry points, for a batch whose solves have been enqueued
+ * already (e.g. a host batch streamed in chunks on several streams, all joined into `stream`). */
+int klujax_cuda_reseed_failed_f64(int transpose, int n_lhs, int n_lhs_A, int n_lhs_b, int n_col,
+                                  int n_rhs, int n_nz, const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                  const double* Ax_dev, const double* b_dev, double* x_dev,
+                                  int32_t* status_dev, double* growth_dev, int32_t* first_bad_out,
+                                  int32_t* n_redone_out, void* stream);
+int klujax_cuda_reseed_failed_c128(int transpose, int n_lhs, int n_lhs_A, int n_lhs_b, int n_col,
+                                   int n_rhs, int n_nz, const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                   const double* Ax_dev, const double* b_dev, double* x_dev,
+                                   int32_t* status_dev, double* growth_dev, int32_t* first_bad_out,
+                                   int32_t* n_redone_out, void* stream);
+
 /* ---- factor_* : klujax.cpp:638-731 --------------------------------------- */
 /* numeric_out_host[n_lhs] receives the handles (host array: see INTEGRATION.md). */
 int klujax_cuda_factor_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai_dev,
@@ -93,7 +146,24 @@ int klujax_cuda_factor_c128(uint64_t symbolic, int n_lhs, int n_nz, const int32_
                             const int32_t* Aj_dev, const double* Ax_dev, uint64_t* numeric_out_host,
                             int32_t* status_dev, double* growth_dev, void* stream);
 
-/* ---- refactor_* : klujax.cpp:733-833 (in place; output handles = input handles) */
+/* The entry a shim binds for `factor`: check != 0 restores the reference's semantics (klu_factor
+ * pivots every system, klujax.cpp:679): the stream is synchronised and systems whose pivot-parity
+ * certificate failed are factorized again in a child batch with a pivot sequence seeded from one
+ * of them; the handles returned may then point into several batches (every entry point accepts
+ * such mixed arrays).  On failure everything is freed (klujax.cpp:684-687), the status of the
+ * first failing system is returned and *first_bad_out is its index. */
+int klujax_cuda_factor_ex_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai_dev,
+                              const int32_t* Aj_dev, const double* Ax_dev, uint64_t* numeric_out_host,
+                              int32_t* status_dev, double* growth_dev, int check,
+                              int32_t* first_bad_out, void* stream);
+int klujax_cuda_factor_ex_c128(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai_dev,
+                               const int32_t* Aj_dev, const double* Ax_dev, uint64_t* numeric_out_host,
+                               int32_t* status_dev, double* growth_dev, int check,
+                               int32_t* first_bad_out, void* stream);
+
+/* ---- refactor_* : klujax.cpp:733-833 (in place; output handles = input handles).  klu_refactor
+ * keeps the pivot order of the handle and never re-pivots: status is 0 or 1 here, growth is
+ * reported for information only. */
 int klujax_cuda_refactor_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai_dev,
                              const int32_t* Aj_dev, const double* Ax_dev,
                              const uint64_t* numeric_in_host, uint64_t* numeric_out_host,
@@ -136,6 +206,55 @@ int klujax_cuda_tsolve_with_numeric_c128(uint64_t symbolic, int n_numeric,
 
 /* ---- free_numeric : klujax.cpp:1273-1291 --------------------------------- */
 int klujax_cuda_free_numeric(int n, const uint64_t* numeric_host, int32_t* freed_out);
+
+/* ---- the same entry points with DEVICE-resident handle arrays -------------------------------
+ * On the CUDA platform XLA delivers `numeric` as a u64[n_lhs] device buffer (klujax.cpp:392-395,
+ * :690, :1044 read it on the host).  Output handles are written stream-ordered, without a
+ * synchronisation.  Input handles must be known on the host to pick the batch and its schedule:
+ * they are copied back, 8 bytes per system and ONE stream synchronisation per call. */
+int klujax_cuda_factor_dev_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai_dev,
+                               const int32_t* Aj_dev, const double* Ax_dev, uint64_t* numeric_out_dev,
+                               int32_t* status_dev, double* growth_dev, int check,
+                               int32_t* first_bad_out, void* stream);
+int klujax_cuda_factor_dev_c128(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai_dev,
+                                const int32_t* Aj_dev, const double* Ax_dev, uint64_t* numeric_out_dev,
+                                int32_t* status_dev, double* growth_dev, int check,
+                                int32_t* first_bad_out, void* stream);
+int klujax_cuda_refactor_dev_f64(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz,
+                                 const int32_t* Ai_dev, const int32_t* Aj_dev, const double* Ax_dev,
+                                 const double* b_unused, const uint64_t* numeric_in_dev, double* x_unused,
+                                 uint64_t* numeric_out_dev, int32_t* status_dev, double* growth_dev,
+                                 void* stream);
+int klujax_cuda_refactor_dev_c128(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz,
+                                  const int32_t* Ai_dev, const int32_t* Aj_dev, const double* Ax_dev,
+                                  const double* b_unused, const uint64_t* numeric_in_dev, double* x_unused,
+                                  uint64_t* numeric_out_dev, int32_t* status_dev, double* growth_dev,
+                                  void* stream);
+int klujax_cuda_refactor_and_solve_dev_f64(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz,
+                                           const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                           const double* Ax_dev, const double* b_dev,
+                                           const uint64_t* numeric_in_dev, double* x_dev,
+                                           uint64_t* numeric_out_dev, int32_t* status_dev,
+                                           double* growth_dev, void* stream);
+int klujax_cuda_refactor_and_solve_dev_c128(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz,
+                                            const int32_t* Ai_dev, const int32_t* Aj_dev,
+                                            const double* Ax_dev, const double* b_dev,
+                                            const uint64_t* numeric_in_dev, double* x_dev,
+                                            uint64_t* numeric_out_dev, int32_t* status_dev,
+                                            double* growth_dev, void* stream);
+int klujax_cuda_solve_with_numeric_dev_f64(uint64_t symbolic, int n_numeric, const uint64_t* numeric_dev,
+                                           int n_lhs_b, int n_col, int n_rhs, const double* b_dev,
+                                           double* x_dev, void* stream);
+int klujax_cuda_solve_with_numeric_dev_c128(uint64_t symbolic, int n_numeric, const uint64_t* numeric_dev,
+                                            int n_lhs_b, int n_col, int n_rhs, const double* b_dev,
+                                            double* x_dev, void* stream);
+int klujax_cuda_tsolve_with_numeric_dev_f64(uint64_t symbolic, int n_numeric, const uint64_t* numeric_dev,
+                                            int n_lhs_b, int n_col, int n_rhs, const double* b_dev,
+                                            double* x_dev, void* stream);
+int klujax_cuda_tsolve_with_numeric_dev_c128(uint64_t symbolic, int n_numeric, const uint64_t* numeric_dev,
+                                             int n_lhs_b, int n_col, int n_rhs, const double* b_dev,
+                                             double* x_dev, void* stream);
+int klujax_cuda_free_numeric_dev(int n, const uint64_t* numeric_dev, int32_t* freed_out, void* stream);
 
 /* ---- dot_f64 / dot_c128 : klujax.cpp:165-249 (batched COO SpMM, "next" row f1) */
 int klujax_cuda_dot_f64(int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai_dev,

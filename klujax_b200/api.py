@@ -93,50 +93,31 @@ def _raise_if_failed(status: torch.Tensor, what: str, check: bool) -> None:
 
 
 GROWTH_LIMIT = 1000.0 * (1.0 + 1e-9)  # 1 / tol of KLU's pivot rule (klu_defaults: tol = 1e-3)
-_RESEED_ROUNDS = 8
+PIVOT_DRIFT = 2  # status: the pivot-parity certificate failed (include/klujax_cuda.h)
 
 
-def _reseed_failed_certificates(fn: str, cx: bool, Ai_t, Aj_t, Ax_d, b_d, x, st, gr, n: int) -> int:
-    """Pivot parity, second line of defence.  The batch runs with the pivot sequence of its
-    first system; `growth = max |L|` certifies per system that KLU's own partial pivoting
-    (diagonal kept iff >= tol * column max, klu_factor as called at klujax.cpp:310/441) would
-    have kept those pivots.  Systems whose certificate fails (growth > 1/tol) are solved again,
-    still on the GPU, with a pivot sequence seeded from one of THEM (a fresh symbolic handle),
-    until every system is certified or _RESEED_ROUNDS is reached.  Returns how many systems
-    were re-solved.  Needs per-system values (a broadcast Ax has one certificate)."""
-    if Ax_d.shape[0] != b_d.shape[0] or Ax_d.shape[0] < 2:
-        return 0
-    # also systems that hit an exactly zero pivot: with its own row exchanges klu_factor may
-    # still succeed on them (if not, seeding from that system reports KLU_SINGULAR like it)
-    sub = torch.nonzero(((gr > GROWTH_LIMIT) & (st == 0)) | (st == 1)).reshape(-1)
-    if sub.numel() == 0:
-        return 0
-    Ai_h = np.ascontiguousarray(Ai_t.detach().cpu().numpy(), dtype=np.int32)
-    Aj_h = np.ascontiguousarray(Aj_t.detach().cpu().numpy(), dtype=np.int32)
-    Ai_d, Aj_d = _indices(Ai_t), _indices(Aj_t)
-    f = getattr(_cabi.lib(), f"klujax_cuda_{fn}_{_suffix(cx)}")
-    redone = 0
-    for _ in range(_RESEED_ROUNDS):
-        if sub.numel() == 0:
-            break
-        Ls = int(sub.numel())
-        Ax_s, b_s = Ax_d[sub].contiguous(), b_d[sub].contiguous()
-        x_s = torch.empty_like(b_s)
-        st_s = torch.empty(Ls, dtype=torch.int32, device=x.device)
-        gr_s = torch.empty(Ls, dtype=torch.float64, device=x.device)
-        h = _cabi.analyze(Ai_h, Aj_h, n)
-        try:
-            _cabi.check(f(C.c_uint64(h), Ls, n, b_d.shape[2], Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d),
-                          _ptr(Ax_s), _ptr(b_s), _ptr(x_s), _ptr(st_s), _ptr(gr_s), _stream()))
-            torch.cuda.current_stream().synchronize()
-        finally:
-            _cabi.free_symbolic(h)
-        x[sub], st[sub], gr[sub] = x_s, st_s, gr_s
-        redone += Ls
-        again = ((gr_s > GROWTH_LIMIT) & (st_s == 0)) | (st_s == 1)
-        again[0] = False  # the seed system carries its own pivot sequence
-        sub = sub[again]
-    return redone
+def _bcast(t: torch.Tensor):
+    """A batch axis that `_canonical` expanded from one entry is passed as ONE entry (the kernels
+    take stride 0): no copy of a broadcast matrix / right-hand side."""
+    if t.shape[0] > 1 and t.stride(0) == 0:
+        return t[:1], 1
+    return t, t.shape[0]
+
+
+def _check_and_reseed(fn: str, cx: bool, L: int, nA: int, nb: int, n: int, r: int, nz: int,
+                      Ai_d, Aj_d, Ax_d, b_d, x, st, gr) -> int:
+    """`check=True` of the fused solves, below the C-ABI (klujax_cuda_reseed_failed_*): systems whose
+    pivot-parity certificate failed are solved again with a pivot sequence seeded from one of them;
+    raises like the reference on the first system that still fails (klujax.cpp:311-314).
+    Returns how many systems were solved again."""
+    f = getattr(_cabi.lib(), f"klujax_cuda_reseed_failed_{_suffix(cx)}")
+    fb, nr = C.c_int32(-1), C.c_int32(0)
+    rc = f(int(fn.startswith("tsolve")), L, nA, nb, n, r, nz, _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d), _ptr(b_d),
+           _ptr(x), _ptr(st), _ptr(gr), C.byref(fb), C.byref(nr), _stream())
+    if rc != 0:
+        msg = _cabi.lib().klujax_cuda_last_error().decode()
+        raise KlujaxCudaError(rc, f"{msg} at system {fb.value}" if fb.value >= 0 else msg)
+    return nr.value
 
 
 def _canonical(Ax: torch.Tensor, x: torch.Tensor, x_name: str):
@@ -303,12 +284,16 @@ def _solve_symbol(fn: str, Ai, Aj, Ax, b, symbolic, check: bool, out=None):
                 or out.numel() != b_t.numel() or not out.is_contiguous()):
             raise ValueError("out must be a contiguous CPU tensor with the shape and dtype of the result")
         out_v = out.view(L, n, r)
+    nA, nb = L, L
     if not host_batch:
-        Ax_d, b_d = _values(Ax_t, cx), _values(b_t, cx)
-        x = torch.empty_like(b_d)
+        Ax_b, nA = _bcast(Ax_t)
+        b_b, nb = _bcast(b_t)
+        Ax_d, b_d = _values(Ax_b, cx), _values(b_b, cx)
+        x = torch.empty((L, n, r), dtype=vdt, device=Ax_d.device)
         st, gr = _new_status(L)
-        _cabi.check(f(C.c_uint64(sym), L, n, r, nz, _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d),
-                      _ptr(b_d), _ptr(x), _ptr(st), _ptr(gr), _stream()))
+        fex = getattr(_cabi.lib(), f"klujax_cuda_{fn}_ex_{_suffix(cx)}")
+        _cabi.check(fex(C.c_uint64(sym), L, nA, nb, n, r, nz, _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d),
+                        _ptr(b_d), _ptr(x), _ptr(st), _ptr(gr), 0, None, None, _stream()))
         if out_v is not None:
             out_v.copy_(x, non_blocking=True)
     else:
@@ -340,10 +325,9 @@ def _solve_symbol(fn: str, Ai, Aj, Ax, b, symbolic, check: bool, out=None):
         for t in (Ax_d, b_d, x, st, gr, Ai_d, Aj_d):
             for s in streams:
                 t.record_stream(s)
-    if check and _reseed_failed_certificates(fn, cx, Ai_t, Aj_t, Ax_d, b_d, x, st, gr, n):
+    if check and _check_and_reseed(fn, cx, L, nA, nb, n, r, nz, Ai_d, Aj_d, Ax_d, b_d, x, st, gr):
         if out_v is not None:
             out_v.copy_(x, non_blocking=True)
-    _raise_if_failed(st, "klu_factor", check)
     if out_v is not None:
         torch.cuda.current_stream().synchronize()  # the caller may read `out` on return
         return out.view(shape)
@@ -377,8 +361,8 @@ def solve(Ai, Aj, Ax, b, check: bool = True) -> torch.Tensor:
     _cabi.check(f(L, n, r, int(Ai_h.size), _cabi.i32p(Ai_h), _cabi.i32p(Aj_h), _ptr(Ax_d), _ptr(b_d),
                   _ptr(x), _ptr(st), _ptr(gr), _stream()))
     if check:
-        _reseed_failed_certificates("solve_with_symbol", cx, Ai_t, Aj_t, Ax_d, b_d, x, st, gr, n)
-    _raise_if_failed(st, "klu_factor", check)
+        _check_and_reseed("solve_with_symbol", cx, L, L, L, n, r, int(Ai_h.size), _indices(Ai_t), _indices(Aj_t),
+                          Ax_d, b_d, x, st, gr)
     return x.reshape(shape)
 
 
@@ -472,14 +456,17 @@ def factor(Ai, Aj, Ax, symbolic, check: bool = True) -> KLUHandleManager:
     num = np.zeros(L, np.uint64)
     st, gr = _new_status(L)
     sym = int(_handle_value(symbolic).reshape(-1)[0])
-    f = getattr(_cabi.lib(), f"klujax_cuda_factor_{_suffix(cx)}")
-    _cabi.check(f(C.c_uint64(sym), L, Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d),
-                  _cabi.u64p(num), _ptr(st), _ptr(gr), _stream()))
-    try:
-        _raise_if_failed(st, "klu_factor", check)
-    except KlujaxCudaError:
-        _cabi.free_numeric(num)  # the reference frees the partial batch (klujax.cpp:684-687)
-        raise
+    # check=True: the reference's semantics (klu_factor pivots every system, klujax.cpp:679) -
+    # systems whose pivot-parity certificate fails get their own pivot sequence in a child batch,
+    # below the C-ABI; a system that is singular under its own pivoting fails the call and the
+    # partial batch is freed (klujax.cpp:684-687)
+    f = getattr(_cabi.lib(), f"klujax_cuda_factor_ex_{_suffix(cx)}")
+    fb = C.c_int32(-1)
+    rc = f(C.c_uint64(sym), L, Ai_d.numel(), _ptr(Ai_d), _ptr(Aj_d), _ptr(Ax_d),
+           _cabi.u64p(num), _ptr(st), _ptr(gr), int(bool(check)), C.byref(fb), _stream())
+    if rc != 0:
+        msg = _cabi.lib().klujax_cuda_last_error().decode()
+        raise KlujaxCudaError(rc, f"{msg} at system {fb.value}" if fb.value >= 0 else msg)
     return KLUHandleManager(num, free_numeric, owner=True)
 
 

@@ -87,6 +87,7 @@ struct LevelCall {
     double* Rs = nullptr;  // [n][lpad], or [L][n]
     long long lpad = 0;
     int sysmajor = 0;    // layout of V / Rs (see level_run_t)
+    int certify = 1;     // a failed pivot-parity certificate is status 2
     cudaStream_t st = nullptr;
 };
 
@@ -221,8 +222,8 @@ __global__ void __launch_bounds__(1024) lv_factor_coop(const LvArgs a) {
                 v = S::recip(v);
             } else if (kind >= TK_MUL) {
                 v = S::mul(v, __ldcg(V + (long long)rec.y * a.lpad + sm * a.vss));
-                if (kind == TK_MUL_TRACK)
-                    atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v)));
+                if (kind >= TK_MUL_TRACK)  // pivot-parity certificate, weighted by class (plan.hpp)
+                    atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v) * KB_TRACK_W2(kind - TK_MUL_TRACK)));
             }
             *o = v;
         }
@@ -329,8 +330,8 @@ __global__ void __launch_bounds__(1024) lv_factor(const LvArgs a) {
                     v = S::recip(v);
                 } else if (kind >= TK_MUL) {
                     v = S::mul(v, V[(long long)rec.y * a.lpad + sm * a.vss]);
-                    if (kind == TK_MUL_TRACK)
-                        atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v)));
+                    if (kind >= TK_MUL_TRACK)
+                        atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v) * KB_TRACK_W2(kind - TK_MUL_TRACK)));
                 }
                 *o = v;
             }
@@ -429,13 +430,14 @@ __global__ void lv_store_x(int L, int n, int r, typename Sc<T>::V* __restrict__ 
 __global__ void lv_finish_status(int L, const int* __restrict__ bad,
                                  const unsigned long long* __restrict__ growth2,
                                  const int* __restrict__ pattern_bad, int32_t* status,
-                                 double* growth) {
+                                 double* growth, int certify) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= L) return;
-    int st = bad[m] ? 1 : 0;
+    const double g2 = __longlong_as_double((long long)growth2[m]);
+    int st = bad[m] ? 1 : ((g2 <= kGrowthLimit2 || !certify) ? 0 : KLUJAX_PIVOT_DRIFT);
     if (pattern_bad && *pattern_bad) st = -3;
     if (status) status[m] = st;
-    if (growth) growth[m] = sqrt(__longlong_as_double((long long)growth2[m]));
+    if (growth) growth[m] = sqrt(g2);
 }
 
 // Batch columns per CTA: one column each while the batch is smaller than the machine
@@ -567,7 +569,7 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
             lv_factor<T><<<grid, level_threads(pf->max_level_tasks, a.slice), 0, c.st>>>(a);
         }
         lv_finish_status<<<(c.L + 255) / 256, 256, 0, c.st>>>(c.L, bad, growth2, c.pattern_bad,
-                                                            c.status, c.growth);
+                                                            c.status, c.growth, c.certify);
     }
     if (ps) {
         const bool tr = (c.mode == PM_FACTOR_TSOLVE || c.mode == PM_TSOLVE);

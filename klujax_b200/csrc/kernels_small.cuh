@@ -125,6 +125,7 @@ enum SmallFlags : int {
     SF_LOAD_NUMERIC = 8,   // read V (LU) and Rs from the numeric handle
     SF_SCALE_IN = 16,      // X = b[perm] / Rs[perm]       (klu_solve)
     SF_SCALE_OUT = 32,     // x[perm] = X / Rs[perm]       (klu_tsolve)
+    SF_CERTIFY = 64,       // a failed pivot-parity certificate is status 2 (factor; klu_refactor never re-pivots)
 };
 
 struct SmallArgs {
@@ -247,7 +248,10 @@ __device__ __forceinline__ void run_chunk(const SmallArgs& a, int pi, int b0, in
         const V_t d = S::sub(vo, acc);
         V_t t = d;
         if (cw & kCwMul) t = S::mul(d, *slot_lo<T>(Vb, h));
-        if (cw & kCwTrack) gmax = fmax(gmax, (h & 1u) ? S::mag2(t) : 0.0);
+        if (cw & kCwTrack) {  // entry of L: pivot-parity certificate, weighted by class (plan.hpp)
+            const uint32_t cls = (h >> 2) & 3u;
+            gmax = fmax(gmax, (h & 1u) ? S::mag2(t) * KB_TRACK_W2(cls) : 0.0);
+        }
         if (cw & kCwPivot) {
             if (h & 2u) {
                 bad |= S::bad_pivot(d);
@@ -452,7 +456,7 @@ __global__ void __launch_bounds__(544, 1) small_kernel(const __grid_constant__ S
                 const bool anybad = __any_sync(0xffffffffu, bad);
                 for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
                 if (lane == 0) {
-                    int st = anybad ? 1 : 0;
+                    int st = anybad ? 1 : ((gmax <= kGrowthLimit2 || !(a.flags & SF_CERTIFY)) ? 0 : KLUJAX_PIVOT_DRIFT);
                     if (a.pattern_bad && *a.pattern_bad) st = -3;
                     if (a.status) a.status[m] = st;
                     if (a.growth) a.growth[m] = sqrt(gmax);

@@ -27,7 +27,7 @@ constexpr int kLanesPerSystem = 32 * kWarpsPerSystem;
 constexpr int kStepBytes = kLanesPerSystem * 8;           // one step of one system's lanes
 constexpr int kStepsPerChunk = kChunkBytes / kStepBytes;  // 4
 
-enum WideKind : uint32_t { WK_IDLE = 0, WK_SUB = 1, WK_MUL = 2, WK_MUL_TRACK = 3, WK_RECIP = 4 };
+enum WideKind : uint32_t { WK_IDLE = 0, WK_SUB = 1, WK_MUL = 2, WK_MUL_TRACK = 3, WK_RECIP = 4, WK_MUL_TRACK_OFF = 5, WK_MUL_TRACK_DIAG = 6 };
 
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(32 * (kWarpsPerSystem * kMaxWideSystems + 1), 
                                 t = S::fast_recip(t);
                             } else {
                                 t = S::mul(t, *reinterpret_cast<const V_t*>(Vb + ((h >> SHR) & MSK)));
-                                if (kind == WK_MUL_TRACK) gmax = fmax(gmax, S::mag2(t));
+                                if (kind != WK_MUL)  // entry of L: pivot-parity certificate (plan.hpp)
+                                    gmax = fmax(gmax, S::mag2(t) * (kind == WK_MUL_TRACK ? 1.0 : kind == WK_MUL_TRACK_OFF ? 1e6 : 1e12));
                             }
                         }
                         *po = t;
@@ -258,7 +259,8 @@ __global__ void __launch_bounds__(32 * (kWarpsPerSystem * kMaxWideSystems + 1), 
         }
         named_barrier(bar_id, kLanesPerSystem);
         if (active && (a.flags & SF_FACTOR) && tid == 0) {
-            int st = flags[0] ? 1 : 0;
+            const double g2 = __longlong_as_double((long long)flags[1]);
+            int st = flags[0] ? 1 : ((g2 <= kGrowthLimit2 || !(a.flags & SF_CERTIFY)) ? 0 : KLUJAX_PIVOT_DRIFT);
             if (a.pattern_bad && *a.pattern_bad) st = -3;
             if (a.status) a.status[m] = st;
             if (a.growth) a.growth[m] = sqrt(__longlong_as_double((long long)flags[1]));

@@ -123,7 +123,9 @@ struct Symbolic {
 
 struct NumericBatch {
     uint32_t id = 0;
-    Symbolic* sym = nullptr;
+    Symbolic* sym = nullptr;     // pivot sequence + schedules of this batch
+    Symbolic* parent = nullptr;  // the caller's symbolic handle (== sym unless the batch was re-seeded)
+    std::unique_ptr<Symbolic> owned;  // re-seeded batches own their symbolic object
     int is_complex = 0, regime = 0, L = 0, live = 0;
     int64_t lpad = 0;  // level regime: padded batch stride
     int sysmajor = 0;  // level regime: V[system][slot] instead of V[slot][system] (kernels_level.cuh)
@@ -347,6 +349,7 @@ struct Op {
     void* x = nullptr;
     NumericBatch* batch = nullptr;  // store (factor modes) or load (solve modes)
     bool store_numeric = false;
+    bool certify = true;  // false: klu_refactor semantics (the pivot order of the handle is kept, no certificate)
     const int* sysidx_dev = nullptr;
     int32_t* status = nullptr;
     double* growth = nullptr;
@@ -420,7 +423,7 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     a.rc = rc;
     a.nz = op.nz;
     a.flags = (factor ? SF_FACTOR : SF_LOAD_NUMERIC) | (solve ? SF_SOLVE : 0) |
-              (op.store_numeric ? SF_STORE_NUMERIC : 0) |
+              (op.store_numeric ? SF_STORE_NUMERIC : 0) | (op.certify ? SF_CERTIFY : 0) |
               (solve ? (transpose ? SF_SCALE_OUT : SF_SCALE_IN) : 0);
     a.coo_dst = S->cur->coo_dst.as<int>();
     a.pattern_bad = S->cur->bad.as<int>();
@@ -691,6 +694,7 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
     lc.sysidx = op.sysidx_dev;
     lc.status = op.status;
     lc.growth = op.growth;
+    lc.certify = op.certify ? 1 : 0;
     lc.st = op.st;
     lc.n = sd.lay.n;
     lc.n_val = sd.lay.n_val;
@@ -726,6 +730,7 @@ static int new_batch(Symbolic* S, int cx, int L, NumericBatch** out) {
     Seeded& sd = S->seeded[cx];
     auto nb = std::make_unique<NumericBatch>();
     nb->sym = S;
+    nb->parent = S;
     nb->is_complex = cx;
     nb->regime = sd.regime;
     nb->L = L;
@@ -746,13 +751,21 @@ static int new_batch(Symbolic* S, int cx, int L, NumericBatch** out) {
     return 0;
 }
 
-// resolves a host array of handles to (batch, per-system element index)
-static int resolve_numeric(int n, const uint64_t* h, NumericBatch** out, std::vector<int>& idx,
-                           bool& identity) {
-    if (n <= 0) return fail(KLU_INVALID, "empty numeric handle array");
-    idx.resize(n);
+// A handle array may mix elements of several batches (systems that needed their own pivot
+// sequence live in re-seeded child batches): a group = the positions of one batch.
+struct NumGroup {
     NumericBatch* nb = nullptr;
-    identity = true;
+    std::vector<int> pos, el;
+    bool identity() const {  // positions 0..L-1 hold elements 0..L-1 of the whole batch
+        if (static_cast<int>(pos.size()) != nb->L) return false;
+        for (size_t q = 0; q < pos.size(); ++q)
+            if (pos[q] != static_cast<int>(q) || el[q] != static_cast<int>(q)) return false;
+        return true;
+    }
+};
+static int resolve_groups(int n, const uint64_t* h, Symbolic* S, int cx, std::vector<NumGroup>& out) {
+    if (n <= 0) return fail(KLU_INVALID, "empty numeric handle array");
+    out.clear();
     std::lock_guard<std::mutex> g(g_reg_mu);
     for (int m = 0; m < n; ++m) {
         if (h[m] == 0) return fail(KLU_INVALID, "numeric pointer is null");
@@ -760,31 +773,47 @@ static int resolve_numeric(int n, const uint64_t* h, NumericBatch** out, std::ve
         const int el = static_cast<int>(h[m] & 0xffffffffu) - 1;
         auto it = g_batches.find(id);
         if (it == g_batches.end()) return fail(KLU_INVALID, "stale numeric handle");
-        if (nb && it->second != nb)
-            return fail(KLU_INVALID, "numeric handles of different factor calls cannot be mixed");
-        nb = it->second;
+        NumericBatch* nb = it->second;
         if (el < 0 || el >= nb->L || nb->freed[el]) return fail(KLU_INVALID, "stale numeric handle");
-        idx[m] = el;
-        if (el != m) identity = false;
+        if (nb->parent != S || nb->is_complex != cx)
+            return fail(KLU_INVALID, "numeric handle belongs to another symbolic handle / dtype");
+        NumGroup* grp = nullptr;
+        for (NumGroup& q : out)
+            if (q.nb == nb) grp = &q;
+        if (!grp) {
+            out.emplace_back();
+            grp = &out.back();
+            grp->nb = nb;
+        }
+        grp->pos.push_back(m);
+        grp->el.push_back(el);
     }
-    if (n != nb->L) identity = identity && false;
-    *out = nb;
     return 0;
 }
 
-template <typename T>
-static int upload_idx(const std::vector<int>& idx, int L, DevBuf& buf, cudaStream_t st) {
-    // broadcast a single element to L systems, or use the list as it is
-    std::vector<int> full(L);
-    for (int m = 0; m < L; ++m) full[m] = idx.size() == 1 ? idx[0] : idx[m];
-    cudaError_t e = buf.alloc(sizeof(int) * L);
-    if (e != cudaSuccess) return fail(KLU_OUT_OF_MEMORY, cudaGetErrorString(e));
-    e = cudaMemcpyAsync(buf.p, full.data(), sizeof(int) * L, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return fail(KLU_OUT_OF_MEMORY, cudaGetErrorString(e));
-    e = cudaStreamSynchronize(st);  // `full` dies with this scope
-    if (e != cudaSuccess) return fail(KLU_OUT_OF_MEMORY, cudaGetErrorString(e));
-    return 0;
-}
+// index list on the device, stream-ordered: no cudaMalloc, no synchronisation (the copy out of
+// pageable memory is staged before cudaMemcpyAsync returns)
+struct StreamBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    ~StreamBuf() {
+        if (p) cudaFreeAsync(p, st);
+    }
+    cudaError_t alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        return cudaMallocAsync(&p, bytes ? bytes : 16, s);
+    }
+    template <typename U>
+    cudaError_t upload(const std::vector<U>& v, cudaStream_t s) {
+        cudaError_t e = alloc(v.size() * sizeof(U), s);
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(U), cudaMemcpyHostToDevice, s);
+    }
+    template <typename U>
+    U* as() const {
+        return static_cast<U*>(p);
+    }
+};
 
 }  // namespace kb
 
@@ -952,10 +981,23 @@ int klujax_cuda_rowreg_selftest(uint64_t symbolic, int is_complex, int transpose
 }
 
 // ---- fused factor + (t)solve ------------------------------------------------
+static int do_solve_with_symbol_strided(int cx, int transpose, uint64_t symbolic, int n_lhs, int n_col, int n_rhs,
+                                        int n_nz, const int32_t* Ai, const int32_t* Aj, const double* Ax,
+                                        long long ax_stride, const double* b, long long b_stride, double* x,
+                                        int32_t* status, double* growth, void* stream);
 static int do_solve_with_symbol(int cx, int transpose, uint64_t symbolic, int n_lhs, int n_col,
                                 int n_rhs, int n_nz, const int32_t* Ai, const int32_t* Aj,
                                 const double* Ax, const double* b, double* x, int32_t* status,
                                 double* growth, void* stream) {
+    return do_solve_with_symbol_strided(cx, transpose, symbolic, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, n_nz, b,
+                                        static_cast<long long>(n_col) * n_rhs, x, status, growth, stream);
+}
+
+// ax_stride / b_stride in elements; 0 = one matrix / one right-hand side for the whole batch
+static int do_solve_with_symbol_strided(int cx, int transpose, uint64_t symbolic, int n_lhs, int n_col, int n_rhs,
+                                        int n_nz, const int32_t* Ai, const int32_t* Aj, const double* Ax,
+                                        long long ax_stride, const double* b, long long b_stride, double* x,
+                                        int32_t* status, double* growth, void* stream) {
     Symbolic* S = sym_of(symbolic);
     if (!S) return fail(KLU_INVALID, "symbolic pointer is null");
     if (n_col != S->ord.n) return fail(KLU_INVALID, "n_col differs from the analysed matrix");
@@ -968,15 +1010,131 @@ static int do_solve_with_symbol(int cx, int transpose, uint64_t symbolic, int n_
     op.Ai = Ai;
     op.Aj = Aj;
     op.Ax = Ax;
-    op.ax_stride = n_nz;
+    op.ax_stride = ax_stride;
     op.b = b;
-    op.b_stride = static_cast<long long>(n_col) * n_rhs;
+    op.b_stride = b_stride;
     op.x = x;
     op.status = status;
     op.growth = growth;
     op.st = static_cast<cudaStream_t>(stream);
     return run_numeric(S, cx, op);
 }
+
+// ---- pivot parity, second line of defence: re-seed below the C-ABI ---------------------------
+// The batch runs with ONE static pivot sequence (seeded from the first system the symbolic handle
+// ever factorized); status 2 (KLUJAX_PIVOT_DRIFT) marks the systems for which KLU's own threshold
+// pivoting (klu_factor per system, klujax.cpp:310/441) would have chosen other pivots, status 1 a
+// pivot that is exactly zero with the static sequence.  Those systems are solved again, on the
+// GPU, with a pivot sequence seeded from one of THEM (a temporary symbolic object), round after
+// round.  This synchronises the stream - it is what `check` semantics cost anyway.
+}  // extern "C" (templates follow)
+namespace {
+template <typename V>
+__global__ void gather_rows_kernel(const V* __restrict__ src, long long src_stride, const int* __restrict__ idx,
+                                   int rows, long long cols, V* __restrict__ dst) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= rows * cols) return;
+    const long long rw = t / cols, c = t - rw * cols;
+    dst[t] = src[(long long)idx[rw] * src_stride + c];
+}
+template <typename V>
+__global__ void scatter_rows_kernel(const V* __restrict__ src, const int* __restrict__ idx, int rows, long long cols,
+                                    V* __restrict__ dst) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= rows * cols) return;
+    const long long rw = t / cols, c = t - rw * cols;
+    dst[(long long)idx[rw] * cols + c] = src[t];
+}
+constexpr int kReseedRounds = 8;
+}  // namespace
+
+static int do_solve_with_symbol_strided(int cx, int transpose, uint64_t symbolic, int n_lhs, int n_col, int n_rhs,
+                                        int n_nz, const int32_t* Ai, const int32_t* Aj, const double* Ax,
+                                        long long ax_stride, const double* b, long long b_stride, double* x,
+                                        int32_t* status, double* growth, void* stream);
+
+// returns 0, or the status of the first system that still fails; *first_bad = its index
+template <typename V>
+static int reseed_failed(int cx, int transpose, int L, int n, int r, int nz, const int32_t* Ai_dev,
+                         const int32_t* Aj_dev, const V* Ax, long long ax_stride, const V* b, long long b_stride,
+                         V* x, int32_t* status, double* growth, cudaStream_t st, int* n_redone, int* first_bad) {
+    if (n_redone) *n_redone = 0;
+    if (first_bad) *first_bad = -1;
+    std::vector<int32_t> hst(L);
+    CUDA_OK(cudaMemcpyAsync(hst.data(), status, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<int> sub;
+    for (int m = 0; m < L; ++m)
+        if (hst[m] == KLUJAX_PIVOT_DRIFT || hst[m] == KLU_SINGULAR) sub.push_back(m);
+    if (!sub.empty()) {
+        std::vector<int> Ai(nz), Aj(nz);
+        CUDA_OK(cudaMemcpyAsync(Ai.data(), Ai_dev, sizeof(int) * nz, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(Aj.data(), Aj_dev, sizeof(int) * nz, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        const long long xcols = static_cast<long long>(n) * r;
+        for (int round = 0; round < kReseedRounds && !sub.empty(); ++round) {
+            const int Ls = static_cast<int>(sub.size());
+            DevBuf d_idx, d_ax, d_b, d_x, d_st, d_gr;
+            CUDA_OK(d_idx.upload(sub));
+            // a broadcast matrix (ax_stride 0) has ONE certificate: the whole call is redone
+            const bool ax_b = ax_stride == 0, b_b = b_stride == 0;
+            if (!ax_b) CUDA_OK(d_ax.alloc(sizeof(V) * static_cast<size_t>(Ls) * nz));
+            if (!b_b) CUDA_OK(d_b.alloc(sizeof(V) * static_cast<size_t>(Ls) * xcols));
+            CUDA_OK(d_x.alloc(sizeof(V) * static_cast<size_t>(Ls) * xcols));
+            CUDA_OK(d_st.alloc(sizeof(int32_t) * Ls));
+            CUDA_OK(d_gr.alloc(sizeof(double) * Ls));
+            const int T = 256;
+            if (!ax_b)
+                gather_rows_kernel<V><<<static_cast<unsigned>((static_cast<long long>(Ls) * nz + T - 1) / T), T, 0, st>>>(
+                    Ax, ax_stride, d_idx.as<int>(), Ls, nz, d_ax.as<V>());
+            if (!b_b)
+                gather_rows_kernel<V><<<static_cast<unsigned>((static_cast<long long>(Ls) * xcols + T - 1) / T), T, 0, st>>>(
+                    b, b_stride, d_idx.as<int>(), Ls, xcols, d_b.as<V>());
+            uint64_t h = 0;
+            int rc = klujax_cuda_analyze(n, nz, Ai.data(), Aj.data(), &h);
+            if (rc) return rc;
+            rc = do_solve_with_symbol_strided(cx, transpose, h, Ls, n, r, nz, Ai_dev, Aj_dev,
+                                              reinterpret_cast<const double*>(ax_b ? Ax : d_ax.as<V>()), ax_b ? 0 : nz,
+                                              reinterpret_cast<const double*>(b_b ? b : d_b.as<V>()), b_b ? 0 : xcols,
+                                              reinterpret_cast<double*>(d_x.as<V>()), d_st.as<int32_t>(),
+                                              d_gr.as<double>(), st);
+            std::vector<int32_t> st_s(Ls, 0);
+            if (!rc) {
+                scatter_rows_kernel<V><<<static_cast<unsigned>((static_cast<long long>(Ls) * xcols + T - 1) / T), T, 0, st>>>(
+                    d_x.as<V>(), d_idx.as<int>(), Ls, xcols, x);
+                scatter_rows_kernel<int32_t><<<(Ls + T - 1) / T, T, 0, st>>>(d_st.as<int32_t>(), d_idx.as<int>(), Ls, 1, status);
+                if (growth)
+                    scatter_rows_kernel<double><<<(Ls + T - 1) / T, T, 0, st>>>(d_gr.as<double>(), d_idx.as<int>(), Ls, 1, growth);
+                cudaMemcpyAsync(st_s.data(), d_st.p, sizeof(int32_t) * Ls, cudaMemcpyDeviceToHost, st);
+            }
+            cudaStreamSynchronize(st);
+            int32_t dummy = 0;
+            klujax_cuda_free_symbolic(h, &dummy);
+            if (rc == KLU_SINGULAR) {
+                // the seed system of this round is singular under KLU's own pivoting: final
+                hst[sub[0]] = KLU_SINGULAR;
+                sub.erase(sub.begin());
+                continue;
+            }
+            if (rc) return rc;
+            if (n_redone) *n_redone += Ls;
+            std::vector<int> again;
+            for (int q = 0; q < Ls; ++q) {
+                hst[sub[q]] = st_s[q];
+                // the seed system (q == 0) carries its own pivot sequence: its verdict is final
+                if (q > 0 && (st_s[q] == KLUJAX_PIVOT_DRIFT || st_s[q] == KLU_SINGULAR)) again.push_back(sub[q]);
+            }
+            sub.swap(again);
+        }
+    }
+    for (int m = 0; m < L; ++m)
+        if (hst[m] != 0) {
+            if (first_bad) *first_bad = m;
+            return hst[m];
+        }
+    return 0;
+}
+extern "C" {
 
 #define DEF_SWS(name, cx, tr)                                                                       \
     int name(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai,       \
@@ -989,6 +1147,79 @@ DEF_SWS(klujax_cuda_solve_with_symbol_f64, 0, 0)
 DEF_SWS(klujax_cuda_solve_with_symbol_c128, 1, 0)
 DEF_SWS(klujax_cuda_tsolve_with_symbol_f64, 0, 1)
 DEF_SWS(klujax_cuda_tsolve_with_symbol_c128, 1, 1)
+
+// The entry an XLA-FFI shim binds: broadcasting of a single matrix or a single
+// right-hand side without materialising it (klujax.py:1844-1848), and - with check != 0 - the
+// reference's error behaviour: synchronise, re-seed the systems whose pivot certificate failed,
+// return the status of the first system that still fails (klujax.cpp:311-314 aborts the batch).
+static int do_reseed_failed(int cx, int transpose, int n_lhs, int n_lhs_A, int n_lhs_b, int n_col, int n_rhs, int n_nz,
+                            const int32_t* Ai, const int32_t* Aj, const double* Ax, const double* b, double* x,
+                            int32_t* status, double* growth, int32_t* first_bad, int32_t* n_redone, void* stream);
+static int do_solve_with_symbol_ex(int cx, int transpose, uint64_t symbolic, int n_lhs, int n_lhs_A, int n_lhs_b,
+                                   int n_col, int n_rhs, int n_nz, const int32_t* Ai, const int32_t* Aj,
+                                   const double* Ax, const double* b, double* x, int32_t* status, double* growth,
+                                   int check, int32_t* first_bad, int32_t* n_redone, void* stream) {
+    if (first_bad) *first_bad = -1;
+    if (n_redone) *n_redone = 0;
+    if ((n_lhs_A != n_lhs && n_lhs_A != 1) || (n_lhs_b != n_lhs && n_lhs_b != 1))
+        return fail(KLU_INVALID, "n_lhs_A / n_lhs_b must be n_lhs or 1");
+    const long long axs = (n_lhs_A == 1 && n_lhs > 1) ? 0 : n_nz;
+    const long long bs = (n_lhs_b == 1 && n_lhs > 1) ? 0 : static_cast<long long>(n_col) * n_rhs;
+    if (check && (!status || !growth)) return fail(KLU_INVALID, "check needs the status and growth arrays");
+    int rc = do_solve_with_symbol_strided(cx, transpose, symbolic, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, axs, b, bs,
+                                          x, status, growth, stream);
+    if (rc || !check || n_lhs <= 0 || n_rhs <= 0) return rc;
+    return do_reseed_failed(cx, transpose, n_lhs, n_lhs_A, n_lhs_b, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, x, status, growth,
+                            first_bad, n_redone, stream);
+}
+#define DEF_SWS_EX(name, cx, tr)                                                                              \
+    int name(uint64_t symbolic, int n_lhs, int n_lhs_A, int n_lhs_b, int n_col, int n_rhs, int n_nz,          \
+             const int32_t* Ai, const int32_t* Aj, const double* Ax, const double* b, double* x,               \
+             int32_t* status, double* growth, int check, int32_t* first_bad, int32_t* n_redone, void* stream) { \
+        return do_solve_with_symbol_ex(cx, tr, symbolic, n_lhs, n_lhs_A, n_lhs_b, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, \
+                                       x, status, growth, check, first_bad, n_redone, stream);                 \
+    }
+// check + re-seed of a batch that has been enqueued already (host batches streamed in chunks)
+static int do_reseed_failed(int cx, int transpose, int n_lhs, int n_lhs_A, int n_lhs_b, int n_col, int n_rhs, int n_nz,
+                            const int32_t* Ai, const int32_t* Aj, const double* Ax, const double* b, double* x,
+                            int32_t* status, double* growth, int32_t* first_bad, int32_t* n_redone, void* stream) {
+    if (first_bad) *first_bad = -1;
+    if (n_redone) *n_redone = 0;
+    if (n_lhs <= 0 || n_rhs <= 0) return 0;
+    if (!status) return fail(KLU_INVALID, "reseed_failed needs the status array");
+    const long long axs = (n_lhs_A == 1 && n_lhs > 1) ? 0 : n_nz;
+    const long long bs = (n_lhs_b == 1 && n_lhs > 1) ? 0 : static_cast<long long>(n_col) * n_rhs;
+    int fb = -1, nr = 0, rc;
+    if (cx)
+        rc = reseed_failed<double2>(1, transpose, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, reinterpret_cast<const double2*>(Ax),
+                                    axs, reinterpret_cast<const double2*>(b), bs, reinterpret_cast<double2*>(x), status,
+                                    growth, static_cast<cudaStream_t>(stream), &nr, &fb);
+    else
+        rc = reseed_failed<double>(0, transpose, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, axs, b, bs, x, status, growth,
+                                   static_cast<cudaStream_t>(stream), &nr, &fb);
+    if (first_bad) *first_bad = fb;
+    if (n_redone) *n_redone = nr;
+    if (rc == KLUJAX_PIVOT_DRIFT) return fail(rc, "klu_factor: the pivot sequence could not be certified");
+    if (rc == KLU_INVALID && fb >= 0) return fail(rc, "entry outside the analysed sparsity pattern or index out of range");
+    if (rc > 0) return fail(rc, "klu_factor failed (singular matrix?)");
+    return rc;
+}
+int klujax_cuda_reseed_failed_f64(int transpose, int n_lhs, int n_lhs_A, int n_lhs_b, int n_col, int n_rhs, int n_nz,
+                                  const int32_t* Ai, const int32_t* Aj, const double* Ax, const double* b, double* x,
+                                  int32_t* status, double* growth, int32_t* first_bad, int32_t* n_redone, void* stream) {
+    return do_reseed_failed(0, transpose, n_lhs, n_lhs_A, n_lhs_b, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, x, status, growth,
+                            first_bad, n_redone, stream);
+}
+int klujax_cuda_reseed_failed_c128(int transpose, int n_lhs, int n_lhs_A, int n_lhs_b, int n_col, int n_rhs, int n_nz,
+                                   const int32_t* Ai, const int32_t* Aj, const double* Ax, const double* b, double* x,
+                                   int32_t* status, double* growth, int32_t* first_bad, int32_t* n_redone, void* stream) {
+    return do_reseed_failed(1, transpose, n_lhs, n_lhs_A, n_lhs_b, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, x, status, growth,
+                            first_bad, n_redone, stream);
+}
+DEF_SWS_EX(klujax_cuda_solve_with_symbol_ex_f64, 0, 0)
+DEF_SWS_EX(klujax_cuda_solve_with_symbol_ex_c128, 1, 0)
+DEF_SWS_EX(klujax_cuda_tsolve_with_symbol_ex_f64, 0, 1)
+DEF_SWS_EX(klujax_cuda_tsolve_with_symbol_ex_c128, 1, 1)
 
 // One-shot `solve` (klujax.cpp:251-380: analyze + factor + solve + free, every call).  The
 // analysis, the pivoting seed factorization and the schedule only depend on the pattern, so the
@@ -1074,9 +1305,59 @@ int klujax_cuda_solve_c128(int n_lhs, int n_col, int n_rhs, int n_nz, const int3
 }
 
 // ---- factor / refactor / refactor_and_solve ---------------------------------
-static int do_factor(int cx, uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai,
-                     const int32_t* Aj, const double* Ax, uint64_t* numeric_out, int32_t* status,
-                     double* growth, void* stream) {
+}  // extern "C" (templates follow)
+// ---- numeric handles: factor / refactor / refactor_and_solve / solves ---------------------------
+static uint64_t handle_of(const NumericBatch* nb, int el) {
+    return (static_cast<uint64_t>(nb->id) << 32) | static_cast<uint64_t>(el + 1);
+}
+// drops one element of a batch (the batch goes when its last element goes)
+static void drop_element(NumericBatch* nb, int el) {
+    bool dead = false;
+    {
+        std::lock_guard<std::mutex> g(g_reg_mu);
+        if (el < 0 || el >= nb->L || nb->freed[el]) return;
+        nb->freed[el] = 1;
+        if (--nb->live == 0) {
+            g_batches.erase(nb->id);
+            dead = true;
+        }
+    }
+    if (dead) {
+        cudaDeviceSynchronize();  // storage may still be read by enqueued work
+        delete nb;
+    }
+}
+
+static int factor_into(Symbolic* S, int cx, NumericBatch* nb, int L, int nz, const int32_t* Ai, const int32_t* Aj,
+                       const void* Ax, long long ax_stride, int32_t* status, double* growth, cudaStream_t st) {
+    Op op;
+    op.mode = PM_FACTOR;
+    op.L = L;
+    op.nz = nz;
+    op.Ai = Ai;
+    op.Aj = Aj;
+    op.Ax = Ax;
+    op.ax_stride = ax_stride;
+    op.batch = nb;
+    op.store_numeric = true;
+    op.status = status;
+    op.growth = growth;
+    op.st = st;
+    return run_numeric(S, cx, op);
+}
+
+// factor_* (klujax.cpp:638-731).  check = 0: enqueue only; every system gets the pivot sequence of
+// the symbolic handle, the certificate is left in status / growth.  check != 0: the reference's
+// semantics - klu_factor pivots every system (klujax.cpp:679) - are restored: systems whose
+// certificate failed are factorized again in a child batch with a pivot sequence seeded from one
+// of THEM (round after round); the returned handles then point into several batches.  A system
+// that is singular under its own pivoting fails the call; like the reference (klujax.cpp:684-687)
+// everything factorized so far is freed.
+template <typename V>
+static int do_factor_t(int cx, uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai, const int32_t* Aj,
+                       const V* Ax, uint64_t* numeric_out, int32_t* status, double* growth, int check,
+                       int32_t* first_bad, void* stream) {
+    if (first_bad) *first_bad = -1;
     Symbolic* S = sym_of(symbolic);
     if (!S) return fail(KLU_INVALID, "symbolic pointer is null");
     if (n_lhs <= 0 || !numeric_out) return fail(KLU_INVALID, "factor: empty batch");
@@ -1086,88 +1367,323 @@ static int do_factor(int cx, uint64_t symbolic, int n_lhs, int n_nz, const int32
         int e = ensure_seeded_dev(S, cx, n_nz, Ai, Aj, Ax, st);
         if (e) return e;
     }
+    StreamBuf tmp_st, tmp_gr;
+    if (check && !status) {
+        CUDA_OK(tmp_st.alloc(sizeof(int32_t) * n_lhs, st));
+        status = tmp_st.as<int32_t>();
+    }
     NumericBatch* nb = nullptr;
     int e = new_batch(S, cx, n_lhs, &nb);
     if (e) return e;
-    Op op;
-    op.mode = PM_FACTOR;
-    op.L = n_lhs;
-    op.nz = n_nz;
-    op.Ai = Ai;
-    op.Aj = Aj;
-    op.Ax = Ax;
-    op.ax_stride = n_nz;
-    op.batch = nb;
-    op.store_numeric = true;
-    op.status = status;
-    op.growth = growth;
-    op.st = st;
-    e = run_numeric(S, cx, op);
+    e = factor_into(S, cx, nb, n_lhs, n_nz, Ai, Aj, Ax, n_nz, status, growth, st);
     if (e) {
-        std::lock_guard<std::mutex> g(g_reg_mu);
-        g_batches.erase(nb->id);
-        delete nb;
+        for (int m = 0; m < n_lhs; ++m) drop_element(nb, m);
         return e;
     }
+    for (int m = 0; m < n_lhs; ++m) numeric_out[m] = handle_of(nb, m);
+    if (!check) return 0;
+
+    std::vector<int32_t> hst(n_lhs);
+    CUDA_OK(cudaMemcpyAsync(hst.data(), status, sizeof(int32_t) * n_lhs, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<int> sub;
     for (int m = 0; m < n_lhs; ++m)
-        numeric_out[m] = (static_cast<uint64_t>(nb->id) << 32) | static_cast<uint64_t>(m + 1);
+        if (hst[m] == KLUJAX_PIVOT_DRIFT || hst[m] == KLU_SINGULAR) sub.push_back(m);
+    int rc_fatal = 0;
+    if (!sub.empty()) {
+        std::vector<int> hAi(n_nz), hAj(n_nz);
+        CUDA_OK(cudaMemcpyAsync(hAi.data(), Ai, sizeof(int) * n_nz, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(hAj.data(), Aj, sizeof(int) * n_nz, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        for (int round = 0; round < kReseedRounds && !sub.empty() && !rc_fatal; ++round) {
+            const int Ls = static_cast<int>(sub.size());
+            uint64_t h = 0;
+            int rc = klujax_cuda_analyze(S->ord.n, n_nz, hAi.data(), hAj.data(), &h);
+            if (rc) {
+                rc_fatal = rc;
+                break;
+            }
+            std::unique_ptr<Symbolic> child(sym_of(h));
+            StreamBuf d_idx, d_ax, d_st, d_gr;
+            CUDA_OK(d_idx.upload(sub, st));
+            CUDA_OK(d_ax.alloc(sizeof(V) * static_cast<size_t>(Ls) * n_nz, st));
+            CUDA_OK(d_st.alloc(sizeof(int32_t) * Ls, st));
+            CUDA_OK(d_gr.alloc(sizeof(double) * Ls, st));
+            const int T = 256;
+            gather_rows_kernel<V><<<static_cast<unsigned>((static_cast<long long>(Ls) * n_nz + T - 1) / T), T, 0, st>>>(
+                Ax, n_nz, d_idx.as<int>(), Ls, n_nz, d_ax.as<V>());
+            {
+                std::lock_guard<std::mutex> lock(child->mu);
+                rc = ensure_seeded_dev(child.get(), cx, n_nz, Ai, Aj, d_ax.p, st);
+            }
+            if (rc == KLU_SINGULAR) {  // the seed of this round is singular under KLU's own pivoting: final
+                hst[sub[0]] = KLU_SINGULAR;
+                sub.erase(sub.begin());
+                continue;
+            }
+            if (rc) {
+                rc_fatal = rc;
+                break;
+            }
+            NumericBatch* cb = nullptr;
+            rc = new_batch(child.get(), cx, Ls, &cb);
+            if (rc) {
+                rc_fatal = rc;
+                break;
+            }
+            cb->parent = S;
+            Symbolic* C = child.get();
+            cb->owned = std::move(child);
+            rc = factor_into(C, cx, cb, Ls, n_nz, Ai, Aj, d_ax.p, n_nz, d_st.as<int32_t>(), d_gr.as<double>(), st);
+            std::vector<int32_t> st_s(Ls, 0);
+            if (!rc) {
+                scatter_rows_kernel<int32_t><<<(Ls + T - 1) / T, T, 0, st>>>(d_st.as<int32_t>(), d_idx.as<int>(), Ls, 1, status);
+                if (growth)
+                    scatter_rows_kernel<double><<<(Ls + T - 1) / T, T, 0, st>>>(d_gr.as<double>(), d_idx.as<int>(), Ls, 1, growth);
+                cudaMemcpyAsync(st_s.data(), d_st.p, sizeof(int32_t) * Ls, cudaMemcpyDeviceToHost, st);
+            }
+            cudaStreamSynchronize(st);
+            if (rc) {
+                for (int q = 0; q < Ls; ++q) drop_element(cb, q);
+                rc_fatal = rc;
+                break;
+            }
+            std::vector<int> again;
+            for (int q = 0; q < Ls; ++q) {
+                const int m = sub[q];
+                if (st_s[q] == 0) {
+                    drop_element(nb, m);  // the parent batch no longer holds this system
+                    numeric_out[m] = handle_of(cb, q);
+                    hst[m] = 0;
+                } else {
+                    if (q == 0 || (st_s[q] != KLUJAX_PIVOT_DRIFT && st_s[q] != KLU_SINGULAR))
+                        hst[m] = st_s[q];  // the seed carries its own pivots: its verdict is final
+                    else
+                        again.push_back(m);
+                    // not kept in this child batch
+                }
+            }
+            for (int q = 0; q < Ls; ++q)
+                if (st_s[q] != 0) drop_element(cb, q);
+            sub.swap(again);
+        }
+        for (int m : sub) (void)m;  // rounds exhausted: hst keeps the failing status
+    }
+    int bad = -1;
+    for (int m = 0; m < n_lhs && bad < 0; ++m)
+        if (hst[m] != 0) bad = m;
+    if (rc_fatal || bad >= 0) {
+        klujax_cuda_free_numeric(n_lhs, numeric_out, nullptr);
+        for (int m = 0; m < n_lhs; ++m) numeric_out[m] = 0;
+        if (rc_fatal) return rc_fatal;
+        if (first_bad) *first_bad = bad;
+        return fail(hst[bad], hst[bad] == KLUJAX_PIVOT_DRIFT ? "klu_factor: the pivot sequence could not be certified"
+                              : hst[bad] == KLU_INVALID    ? "entry outside the analysed sparsity pattern or index out of range"
+                                                           : "klu_factor failed (singular matrix?)");
+    }
     return 0;
 }
-int klujax_cuda_factor_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai,
-                           const int32_t* Aj, const double* Ax, uint64_t* numeric_out,
-                           int32_t* status, double* growth, void* stream) {
-    return do_factor(0, symbolic, n_lhs, n_nz, Ai, Aj, Ax, numeric_out, status, growth, stream);
-}
-int klujax_cuda_factor_c128(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai,
-                            const int32_t* Aj, const double* Ax, uint64_t* numeric_out,
-                            int32_t* status, double* growth, void* stream) {
-    return do_factor(1, symbolic, n_lhs, n_nz, Ai, Aj, Ax, numeric_out, status, growth, stream);
+static int do_factor(int cx, uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai, const int32_t* Aj,
+                     const double* Ax, uint64_t* numeric_out, int32_t* status, double* growth, int check,
+                     int32_t* first_bad, void* stream) {
+    if (cx)
+        return do_factor_t<double2>(1, symbolic, n_lhs, n_nz, Ai, Aj, reinterpret_cast<const double2*>(Ax), numeric_out,
+                                    status, growth, check, first_bad, stream);
+    return do_factor_t<double>(0, symbolic, n_lhs, n_nz, Ai, Aj, Ax, numeric_out, status, growth, check, first_bad, stream);
 }
 
+// refactor_* / refactor_and_solve_* (klujax.cpp:733-993).  klu_refactor keeps the pivot order of
+// the handle and never re-pivots, so there is no certificate here (status 0 or 1); the handles may
+// point into several batches (see factor).
+template <typename V>
+static int do_refactor_t(int cx, int with_solve, uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz,
+                         const int32_t* Ai, const int32_t* Aj, const V* Ax, const V* b, const uint64_t* numeric_in,
+                         V* x, uint64_t* numeric_out, int32_t* status, double* growth, void* stream) {
+    Symbolic* S = sym_of(symbolic);
+    if (!S) return fail(KLU_INVALID, "symbolic pointer is null");
+    if (!numeric_in) return fail(KLU_INVALID, "numeric pointer is null");
+    std::vector<NumGroup> groups;
+    int e = resolve_groups(n_lhs, numeric_in, S, cx, groups);
+    if (e) return e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long xcols = static_cast<long long>(n_col) * n_rhs;
+    const int T = 256;
+    for (NumGroup& g : groups) {
+        const int Lg = static_cast<int>(g.pos.size());
+        const bool direct = groups.size() == 1 && g.identity();
+        StreamBuf d_pos, d_el, d_ax, d_b, d_x, d_st, d_gr;
+        Op op;
+        op.mode = with_solve ? PM_FACTOR_SOLVE : PM_FACTOR;
+        op.L = Lg;
+        op.r = with_solve ? n_rhs : 0;
+        op.nz = n_nz;
+        op.Ai = Ai;
+        op.Aj = Aj;
+        op.ax_stride = n_nz;
+        op.b_stride = xcols;
+        op.batch = g.nb;
+        op.store_numeric = true;
+        op.certify = false;
+        op.st = st;
+        if (direct) {
+            op.Ax = Ax;
+            op.b = b;
+            op.x = x;
+            op.status = status;
+            op.growth = growth;
+        } else {
+            CUDA_OK(d_pos.upload(g.pos, st));
+            CUDA_OK(d_el.upload(g.el, st));
+            CUDA_OK(d_ax.alloc(sizeof(V) * static_cast<size_t>(Lg) * n_nz, st));
+            CUDA_OK(d_st.alloc(sizeof(int32_t) * Lg, st));
+            CUDA_OK(d_gr.alloc(sizeof(double) * Lg, st));
+            gather_rows_kernel<V><<<static_cast<unsigned>((static_cast<long long>(Lg) * n_nz + T - 1) / T), T, 0, st>>>(
+                Ax, n_nz, d_pos.as<int>(), Lg, n_nz, d_ax.as<V>());
+            op.Ax = d_ax.p;
+            op.sysidx_dev = d_el.as<int>();
+            op.status = d_st.as<int32_t>();
+            op.growth = d_gr.as<double>();
+            if (with_solve) {
+                CUDA_OK(d_b.alloc(sizeof(V) * static_cast<size_t>(Lg) * xcols, st));
+                CUDA_OK(d_x.alloc(sizeof(V) * static_cast<size_t>(Lg) * xcols, st));
+                gather_rows_kernel<V><<<static_cast<unsigned>((static_cast<long long>(Lg) * xcols + T - 1) / T), T, 0, st>>>(
+                    b, xcols, d_pos.as<int>(), Lg, xcols, d_b.as<V>());
+                op.b = d_b.p;
+                op.x = d_x.p;
+            }
+        }
+        e = run_numeric(g.nb->sym, cx, op);
+        if (e) return e;
+        if (!direct) {
+            if (with_solve)
+                scatter_rows_kernel<V><<<static_cast<unsigned>((static_cast<long long>(Lg) * xcols + T - 1) / T), T, 0, st>>>(
+                    d_x.as<V>(), d_pos.as<int>(), Lg, xcols, x);
+            if (status)
+                scatter_rows_kernel<int32_t><<<(Lg + T - 1) / T, T, 0, st>>>(d_st.as<int32_t>(), d_pos.as<int>(), Lg, 1, status);
+            if (growth)
+                scatter_rows_kernel<double><<<(Lg + T - 1) / T, T, 0, st>>>(d_gr.as<double>(), d_pos.as<int>(), Lg, 1, growth);
+        }
+    }
+    if (numeric_out)
+        for (int m = 0; m < n_lhs; ++m) numeric_out[m] = numeric_in[m];  // klujax.cpp:785-786
+    return 0;
+}
 static int do_refactor(int cx, int with_solve, uint64_t symbolic, int n_lhs, int n_col, int n_rhs,
                        int n_nz, const int32_t* Ai, const int32_t* Aj, const double* Ax,
                        const double* b, const uint64_t* numeric_in, double* x,
                        uint64_t* numeric_out, int32_t* status, double* growth, void* stream) {
+    if (cx)
+        return do_refactor_t<double2>(1, with_solve, symbolic, n_lhs, n_col, n_rhs, n_nz, Ai, Aj,
+                                      reinterpret_cast<const double2*>(Ax), reinterpret_cast<const double2*>(b),
+                                      numeric_in, reinterpret_cast<double2*>(x), numeric_out, status, growth, stream);
+    return do_refactor_t<double>(0, with_solve, symbolic, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, numeric_in, x,
+                                 numeric_out, status, growth, stream);
+}
+
+// solve_with_numeric_* / tsolve_with_numeric_* (klujax.cpp:995-1271)
+template <typename V>
+static int do_solve_numeric_t(int cx, int transpose, uint64_t symbolic, int n_numeric, const uint64_t* numeric,
+                              int n_lhs_b, int n_col, int n_rhs, const V* b, V* x, void* stream) {
     Symbolic* S = sym_of(symbolic);
     if (!S) return fail(KLU_INVALID, "symbolic pointer is null");
-    if (!numeric_in) return fail(KLU_INVALID, "numeric pointer is null");
-    NumericBatch* nb = nullptr;
-    std::vector<int> idx;
-    bool identity = false;
-    int e = resolve_numeric(n_lhs, numeric_in, &nb, idx, identity);
+    if (n_col != S->ord.n) return fail(KLU_INVALID, "n_col differs from the analysed matrix");
+    std::vector<NumGroup> groups;
+    int e = resolve_groups(n_numeric, numeric, S, cx, groups);
     if (e) return e;
-    if (nb->sym != S || nb->is_complex != cx)
-        return fail(KLU_INVALID, "numeric handle belongs to another symbolic handle / dtype");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    DevBuf didx;
-    if (!identity) {
-        e = upload_idx<int>(idx, n_lhs, didx, st);
-        if (e) return e;
+    // broadcast rules of klujax.cpp:1044-1059
+    const bool bc_num = (n_numeric == 1), bc_b = (n_lhs_b == 1);
+    int L;
+    if (!bc_num && !bc_b) {
+        if (n_numeric != n_lhs_b) return fail(KLU_INVALID, "numeric and b batch size mismatch");
+        L = n_numeric;
+    } else if (!bc_num) {
+        L = n_numeric;
+    } else if (!bc_b) {
+        L = n_lhs_b;
+    } else {
+        L = 1;
     }
-    Op op;
-    op.mode = with_solve ? PM_FACTOR_SOLVE : PM_FACTOR;
-    op.L = n_lhs;
-    op.r = with_solve ? n_rhs : 0;
-    op.nz = n_nz;
-    op.Ai = Ai;
-    op.Aj = Aj;
-    op.Ax = Ax;
-    op.ax_stride = n_nz;
-    op.b = b;
-    op.b_stride = static_cast<long long>(n_col) * n_rhs;
-    op.x = x;
-    op.batch = nb;
-    op.store_numeric = true;
-    op.sysidx_dev = identity ? nullptr : didx.as<int>();
-    op.status = status;
-    op.growth = growth;
-    op.st = st;
-    e = run_numeric(S, cx, op);
-    if (!identity) cudaStreamSynchronize(st);  // didx is released on return
-    if (e) return e;
-    if (numeric_out)
-        for (int m = 0; m < n_lhs; ++m) numeric_out[m] = numeric_in[m];  // klujax.cpp:785-786
+    if (n_rhs <= 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long xcols = static_cast<long long>(n_col) * n_rhs;
+    const int T = 256;
+    for (NumGroup& g : groups) {
+        int Lg = static_cast<int>(g.pos.size());
+        const bool direct = groups.size() == 1 && !bc_num && g.identity();
+        StreamBuf d_pos, d_el, d_b, d_x;
+        Op op;
+        op.mode = transpose ? PM_TSOLVE : PM_SOLVE;
+        op.r = n_rhs;
+        op.b_stride = bc_b && L > 1 ? 0 : xcols;
+        op.batch = g.nb;
+        op.st = st;
+        if (direct) {
+            op.L = L;
+            op.b = b;
+            op.x = x;
+        } else if (groups.size() == 1) {
+            // one batch, permuted / partial / broadcast element list: systems stay in place
+            std::vector<int> full(L);
+            for (int m = 0; m < L; ++m) full[m] = bc_num ? g.el[0] : g.el[m];
+            CUDA_OK(d_el.upload(full, st));
+            op.L = L;
+            op.b = b;
+            op.x = x;
+            op.sysidx_dev = d_el.as<int>();
+        } else {
+            CUDA_OK(d_pos.upload(g.pos, st));
+            CUDA_OK(d_el.upload(g.el, st));
+            CUDA_OK(d_x.alloc(sizeof(V) * static_cast<size_t>(Lg) * xcols, st));
+            op.L = Lg;
+            op.sysidx_dev = d_el.as<int>();
+            op.x = d_x.p;
+            if (bc_b) {
+                op.b = b;
+                op.b_stride = Lg > 1 ? 0 : xcols;
+            } else {
+                CUDA_OK(d_b.alloc(sizeof(V) * static_cast<size_t>(Lg) * xcols, st));
+                gather_rows_kernel<V><<<static_cast<unsigned>((static_cast<long long>(Lg) * xcols + T - 1) / T), T, 0, st>>>(
+                    b, xcols, d_pos.as<int>(), Lg, xcols, d_b.as<V>());
+                op.b = d_b.p;
+                op.b_stride = xcols;
+            }
+        }
+        e = run_numeric(g.nb->sym, cx, op);
+        if (e) return e;
+        if (groups.size() > 1)
+            scatter_rows_kernel<V><<<static_cast<unsigned>((static_cast<long long>(Lg) * xcols + T - 1) / T), T, 0, st>>>(
+                d_x.as<V>(), d_pos.as<int>(), Lg, xcols, x);
+    }
     return 0;
+}
+static int do_solve_numeric(int cx, int transpose, uint64_t symbolic, int n_numeric,
+                            const uint64_t* numeric, int n_lhs_b, int n_col, int n_rhs,
+                            const double* b, double* x, void* stream) {
+    if (cx)
+        return do_solve_numeric_t<double2>(1, transpose, symbolic, n_numeric, numeric, n_lhs_b, n_col, n_rhs,
+                                           reinterpret_cast<const double2*>(b), reinterpret_cast<double2*>(x), stream);
+    return do_solve_numeric_t<double>(0, transpose, symbolic, n_numeric, numeric, n_lhs_b, n_col, n_rhs, b, x, stream);
+}
+extern "C" {
+int klujax_cuda_factor_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai,
+                           const int32_t* Aj, const double* Ax, uint64_t* numeric_out,
+                           int32_t* status, double* growth, void* stream) {
+    return do_factor(0, symbolic, n_lhs, n_nz, Ai, Aj, Ax, numeric_out, status, growth, 0, nullptr, stream);
+}
+int klujax_cuda_factor_c128(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai,
+                            const int32_t* Aj, const double* Ax, uint64_t* numeric_out,
+                            int32_t* status, double* growth, void* stream) {
+    return do_factor(1, symbolic, n_lhs, n_nz, Ai, Aj, Ax, numeric_out, status, growth, 0, nullptr, stream);
+}
+int klujax_cuda_factor_ex_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai, const int32_t* Aj,
+                              const double* Ax, uint64_t* numeric_out, int32_t* status, double* growth, int check,
+                              int32_t* first_bad, void* stream) {
+    return do_factor(0, symbolic, n_lhs, n_nz, Ai, Aj, Ax, numeric_out, status, growth, check, first_bad, stream);
+}
+int klujax_cuda_factor_ex_c128(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai, const int32_t* Aj,
+                               const double* Ax, uint64_t* numeric_out, int32_t* status, double* growth, int check,
+                               int32_t* first_bad, void* stream) {
+    return do_factor(1, symbolic, n_lhs, n_nz, Ai, Aj, Ax, numeric_out, status, growth, check, first_bad, stream);
 }
 int klujax_cuda_refactor_f64(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai,
                              const int32_t* Aj, const double* Ax, const uint64_t* nin,
@@ -1197,56 +1713,6 @@ int klujax_cuda_refactor_and_solve_c128(uint64_t symbolic, int n_lhs, int n_col,
     return do_refactor(1, 1, symbolic, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, nin, x, nout,
                        status, growth, stream);
 }
-
-// ---- solves with a numeric handle --------------------------------------------
-static int do_solve_numeric(int cx, int transpose, uint64_t symbolic, int n_numeric,
-                            const uint64_t* numeric, int n_lhs_b, int n_col, int n_rhs,
-                            const double* b, double* x, void* stream) {
-    Symbolic* S = sym_of(symbolic);
-    if (!S) return fail(KLU_INVALID, "symbolic pointer is null");
-    if (n_col != S->ord.n) return fail(KLU_INVALID, "n_col differs from the analysed matrix");
-    NumericBatch* nb = nullptr;
-    std::vector<int> idx;
-    bool identity = false;
-    int e = resolve_numeric(n_numeric, numeric, &nb, idx, identity);
-    if (e) return e;
-    if (nb->sym != S || nb->is_complex != cx)
-        return fail(KLU_INVALID, "numeric handle belongs to another symbolic handle / dtype");
-    // broadcast rules of klujax.cpp:1044-1059
-    const bool bc_num = (n_numeric == 1), bc_b = (n_lhs_b == 1);
-    int L;
-    if (!bc_num && !bc_b) {
-        if (n_numeric != n_lhs_b) return fail(KLU_INVALID, "numeric and b batch size mismatch");
-        L = n_numeric;
-    } else if (!bc_num) {
-        L = n_numeric;
-    } else if (!bc_b) {
-        L = n_lhs_b;
-    } else {
-        L = 1;
-    }
-    if (n_rhs <= 0) return 0;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    DevBuf didx;
-    const bool ident = identity && (L == n_numeric);
-    if (!ident) {
-        e = upload_idx<int>(idx, L, didx, st);
-        if (e) return e;
-    }
-    Op op;
-    op.mode = transpose ? PM_TSOLVE : PM_SOLVE;
-    op.L = L;
-    op.r = n_rhs;
-    op.b = b;
-    op.b_stride = bc_b && L > 1 ? 0 : static_cast<long long>(n_col) * n_rhs;
-    op.x = x;
-    op.batch = nb;
-    op.sysidx_dev = ident ? nullptr : didx.as<int>();
-    op.st = st;
-    e = run_numeric(S, cx, op);
-    if (!ident) cudaStreamSynchronize(st);
-    return e;
-}
 #define DEF_SWN(name, cx, tr)                                                                     \
     int name(uint64_t symbolic, int n_numeric, const uint64_t* numeric, int n_lhs_b, int n_col,   \
              int n_rhs, const double* b, double* x, void* stream) {                               \
@@ -1257,6 +1723,71 @@ DEF_SWN(klujax_cuda_solve_with_numeric_f64, 0, 0)
 DEF_SWN(klujax_cuda_solve_with_numeric_c128, 1, 0)
 DEF_SWN(klujax_cuda_tsolve_with_numeric_f64, 0, 1)
 DEF_SWN(klujax_cuda_tsolve_with_numeric_c128, 1, 1)
+
+// ---- device-resident handle arrays (what XLA delivers on the CUDA platform: u64[n_lhs] buffers,
+// klujax.cpp:392-395, :690, :1044) ------------------------------------------------------------------
+// Output handles are written to the device stream-ordered (no synchronisation).  Input handles
+// have to be known on the host to pick the batch and its schedule: they are copied back (8 bytes
+// per system, one stream synchronisation per call - stated in INTEGRATION.md).
+static int fetch_handles(const uint64_t* dev, int n, std::vector<uint64_t>& host, cudaStream_t st) {
+    host.resize(n > 0 ? n : 0);
+    if (n <= 0) return 0;
+    CUDA_OK(cudaMemcpyAsync(host.data(), dev, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+static int push_handles(const std::vector<uint64_t>& host, uint64_t* dev, cudaStream_t st) {
+    if (!dev || host.empty()) return 0;
+    CUDA_OK(cudaMemcpyAsync(dev, host.data(), sizeof(uint64_t) * host.size(), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+#define DEF_FACTOR_DEV(name, cx)                                                                                      \
+    int name(uint64_t symbolic, int n_lhs, int n_nz, const int32_t* Ai, const int32_t* Aj, const double* Ax,          \
+             uint64_t* numeric_out_dev, int32_t* status, double* growth, int check, int32_t* first_bad, void* stream) { \
+        std::vector<uint64_t> h(n_lhs > 0 ? n_lhs : 0, 0);                                                            \
+        int rc = do_factor(cx, symbolic, n_lhs, n_nz, Ai, Aj, Ax, h.data(), status, growth, check, first_bad, stream); \
+        if (rc) return rc;                                                                                            \
+        return push_handles(h, numeric_out_dev, static_cast<cudaStream_t>(stream));                                   \
+    }
+DEF_FACTOR_DEV(klujax_cuda_factor_dev_f64, 0)
+DEF_FACTOR_DEV(klujax_cuda_factor_dev_c128, 1)
+#define DEF_REFACTOR_DEV(name, cx, ws)                                                                               \
+    int name(uint64_t symbolic, int n_lhs, int n_col, int n_rhs, int n_nz, const int32_t* Ai, const int32_t* Aj,     \
+             const double* Ax, const double* b, const uint64_t* numeric_in_dev, double* x, uint64_t* numeric_out_dev, \
+             int32_t* status, double* growth, void* stream) {                                                        \
+        std::vector<uint64_t> h;                                                                                     \
+        int rc = fetch_handles(numeric_in_dev, n_lhs, h, static_cast<cudaStream_t>(stream));                         \
+        if (rc) return rc;                                                                                           \
+        rc = do_refactor(cx, ws, symbolic, n_lhs, n_col, n_rhs, n_nz, Ai, Aj, Ax, b, h.data(), x, nullptr, status,   \
+                         growth, stream);                                                                            \
+        if (rc) return rc;                                                                                           \
+        if (numeric_out_dev && numeric_out_dev != numeric_in_dev)                                                    \
+            CUDA_OK(cudaMemcpyAsync(numeric_out_dev, numeric_in_dev, sizeof(uint64_t) * n_lhs,                       \
+                                    cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));                   \
+        return 0;                                                                                                    \
+    }
+DEF_REFACTOR_DEV(klujax_cuda_refactor_dev_f64, 0, 0)
+DEF_REFACTOR_DEV(klujax_cuda_refactor_dev_c128, 1, 0)
+DEF_REFACTOR_DEV(klujax_cuda_refactor_and_solve_dev_f64, 0, 1)
+DEF_REFACTOR_DEV(klujax_cuda_refactor_and_solve_dev_c128, 1, 1)
+#define DEF_SWN_DEV(name, cx, tr)                                                                                    \
+    int name(uint64_t symbolic, int n_numeric, const uint64_t* numeric_dev, int n_lhs_b, int n_col, int n_rhs,       \
+             const double* b, double* x, void* stream) {                                                             \
+        std::vector<uint64_t> h;                                                                                     \
+        int rc = fetch_handles(numeric_dev, n_numeric, h, static_cast<cudaStream_t>(stream));                        \
+        if (rc) return rc;                                                                                           \
+        return do_solve_numeric(cx, tr, symbolic, n_numeric, h.data(), n_lhs_b, n_col, n_rhs, b, x, stream);         \
+    }
+DEF_SWN_DEV(klujax_cuda_solve_with_numeric_dev_f64, 0, 0)
+DEF_SWN_DEV(klujax_cuda_solve_with_numeric_dev_c128, 1, 0)
+DEF_SWN_DEV(klujax_cuda_tsolve_with_numeric_dev_f64, 0, 1)
+DEF_SWN_DEV(klujax_cuda_tsolve_with_numeric_dev_c128, 1, 1)
+int klujax_cuda_free_numeric_dev(int n, const uint64_t* numeric_dev, int32_t* freed, void* stream) {
+    std::vector<uint64_t> h;
+    int rc = fetch_handles(numeric_dev, n, h, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    return klujax_cuda_free_numeric(n, h.data(), freed);
+}
 
 int klujax_cuda_free_numeric(int n, const uint64_t* numeric, int32_t* freed) {
     if (freed) *freed = 1;  // the reference always reports 1 (klujax.cpp:1290)

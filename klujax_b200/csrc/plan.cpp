@@ -426,7 +426,10 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
                 } else if (s == dg) {
                     lv.add(TK_RECIP, s, -1, pr);
                 } else {
-                    lv.add(TK_MUL_TRACK, s, dg, pr);
+                    uint8_t kind = TK_MUL_TRACK;
+                    if (!piv.diag_cand.empty() && piv.diag_cand[k] != -2)  // off-diagonal static pivot (plan.hpp)
+                        kind = lay.slot_row[s] == piv.diag_cand[k] ? TK_MUL_TRACK_DIAG : TK_MUL_TRACK_OFF;
+                    lv.add(kind, s, dg, pr);
                 }
             }
             for (int s = cb; s < ce; ++s) pos[lay.slot_row[s]] = -1;
@@ -530,10 +533,11 @@ bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram&
     if (out.n_slots > 16383) return false;
     const uint32_t ZERO = out.zero_slot, ONE = ZERO + 1, TRASH = ZERO + 2;
     auto opword = [](uint32_t a, uint32_t b) { return (a << 18) | (b << 4); };
-    auto hdword = [](uint32_t o, uint32_t d, bool track, bool pivot) {
-        return (o << 18) | (d << 4) | (track ? 1u : 0u) | (pivot ? 2u : 0u);
+    // bits 2-3: certificate class of a tracked entry (plan.hpp)
+    auto hdword = [](uint32_t o, uint32_t d, int track, bool pivot) {
+        return (o << 18) | (d << 4) | (track ? 1u : 0u) | (pivot ? 2u : 0u) | (track > 1 ? static_cast<uint32_t>(track - 1) << 2 : 0u);
     };
-    const uint32_t idle_op = opword(ZERO, ZERO), idle_hd = hdword(TRASH, ONE, false, false);
+    const uint32_t idle_op = opword(ZERO, ZERO), idle_hd = hdword(TRASH, ONE, 0, false);
     // a batch = header line + 2*trips operand lines
     const int MAXTRIPS = (LINES - 1) / 2;
     int line = LINES;  // forces a first chunk
@@ -595,8 +599,8 @@ bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram&
                     const uint32_t div = tk.div >= 0 ? static_cast<uint32_t>(tk.div) : ONE;
                     if (tk.kind == TK_RECIP) cw |= kCwPivot;
                     if (tk.div >= 0) cw |= kCwMul;
-                    if (tk.kind == TK_MUL_TRACK) cw |= kCwTrack;
-                    out.stream[base + lead] = hdword(tk.out, div, tk.kind == TK_MUL_TRACK, tk.kind == TK_RECIP);
+                    if (tk.kind >= TK_MUL_TRACK) cw |= kCwTrack;
+                    out.stream[base + lead] = hdword(tk.out, div, tk.kind >= TK_MUL_TRACK ? tk.kind - TK_MUL_TRACK + 1 : 0, tk.kind == TK_RECIP);
                     for (int q = 0; q < tk.plen; ++q) {
                         const int lane = lead + (q % g), row = q / g;
                         out.stream[base + static_cast<size_t>(LW) * (1 + row) + lane] =
@@ -722,7 +726,7 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
             for (size_t k = 0; k < cnt; ++k) {
                 const Task& tk = prog.tasks[order[i + k]];
                 const uint32_t d = tk.div >= 0 ? static_cast<uint32_t>(tk.div) : ONE;
-                const uint32_t kind = tk.kind == TK_RECIP ? 4u : tk.kind == TK_MUL_TRACK ? 3u : tk.kind == TK_MUL ? 2u : 1u;
+                const uint32_t kind = tk.kind == TK_RECIP ? 4u : tk.kind == TK_MUL_TRACK ? 3u : tk.kind == TK_MUL_TRACK_OFF ? 5u : tk.kind == TK_MUL_TRACK_DIAG ? 6u : tk.kind == TK_MUL ? 2u : 1u;
                 // lane k: (header word, operand word) side by side
                 base[2 * k] = (static_cast<uint32_t>(tk.out) << 18) | (d << 4) | (tk.fresh ? 8u : 0u) | kind;
                 base[2 * k + 1] = tk.plen ? (static_cast<uint32_t>(prog.pa[tk.pbeg]) << 18) |

@@ -26,6 +26,13 @@ enum TaskKind : uint8_t {
     TK_RECIP = 2,      // V[out]  = 1 / (V[out] - acc)        (pivot; singularity check)
     TK_MUL = 3,        // V[out]  = (V[out] - acc) * V[div]   (solve with a pivot)
     TK_MUL_TRACK = 4,  // same, and track max |V[out]|        (entry of L: growth certificate)
+    // pivot-parity certificate of a column whose static pivot is NOT the diagonal candidate (KLU
+    // chose the column maximum at seeding time because the diagonal failed the threshold test):
+    // KLU makes the same choice iff no other candidate is larger, |L(i,k)| <= 1, and the diagonal
+    // candidate still fails, |L(diag,k)| < tol.  The tracked magnitude is weighted so that ONE
+    // number certifies every column: growth <= 1/tol = 1000  (weights 1, 1/tol, 1/tol^2).
+    TK_MUL_TRACK_OFF = 5,   // entry of L in such a column:            |L| * 1e3
+    TK_MUL_TRACK_DIAG = 6,  // the diagonal candidate in such a column: |L| * 1e6
 };
 
 struct Task {
@@ -102,6 +109,11 @@ constexpr int kChunkWords = 2048;
 constexpr int kMaxBatches = 1536;  // per program (control words live in the parameter space)
 constexpr int kMaxChunks = 255;
 constexpr uint32_t kCwPivot = 1u << 11, kCwMul = 1u << 12, kCwTrack = 1u << 13;
+// squared weight of a tracked |L|^2 by certificate class (0 diagonal pivot, 1 off-diagonal pivot
+// column, 2 diagonal candidate of such a column); status code of a failed certificate
+#define KB_TRACK_W2(cls) ((cls) == 0 ? 1.0 : (cls) == 1 ? 1e6 : 1e12)
+constexpr int KLUJAX_PIVOT_DRIFT = 2;
+constexpr double kGrowthLimit2 = 1000.0 * 1000.0 * (1.0 + 1e-9);
 struct PackedProgram {
     std::vector<uint32_t> ctrl;       // nbatch
     std::vector<uint16_t> chunk_ptr;  // nchunks + 1

@@ -64,6 +64,7 @@ bool seed_factor(const CscPattern& A, const Ordering& ord, const T* Ax, PivotPla
     plan.Lp.assign(n + 1, 0);
     plan.Up.assign(n + 1, 0);
     plan.Offp.assign(n + 1, 0);
+    plan.diag_cand.assign(n, -2);
     if (A.has_duplicates) {
         plan.status = KLU_INVALID;  // klu_factor's KLU_scale rejects duplicates
         return false;
@@ -241,6 +242,7 @@ bool seed_factor(const CscPattern& A, const Ordering& ord, const T* Ax, PivotPla
             // ---- record the pivot, keeping track of which row is "the diagonal"
             if (pivrow != diagrow) {
                 plan.noffdiag++;
+                plan.diag_cand[k1 + k] = pinv[diagrow] < 0 ? diagrow : -1;  // block-local row for now
                 if (pinv[diagrow] < 0) {
                     const int kbar = flip(pinv[pivrow]);
                     prow[kbar] = diagrow;
@@ -250,6 +252,8 @@ bool seed_factor(const CscPattern& A, const Ordering& ord, const T* Ax, PivotPla
             prow[k] = pivrow;
             pinv[pivrow] = k;
         }
+        for (int k = 0; k < nk; ++k)
+            if (plan.diag_cand[k1 + k] >= 0) plan.diag_cand[k1 + k] = k1 + pinv[plan.diag_cand[k1 + k]];
         // rows of L in pivot order; Pnum through the symbolic permutation
         for (int k = 0; k < nk; ++k) {
             for (int i : Lrow[k]) plan.Li.push_back(pinv[i]);

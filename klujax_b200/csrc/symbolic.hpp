@@ -59,6 +59,11 @@ struct PivotPlan {
     std::vector<int> Offp, Offi;       // BTF off-diagonal entries per column (global pivot rows)
     std::vector<int> Offsrc;           // csc slot each off-diagonal entry comes from
     int noffdiag = 0;
+    // pivot-parity certificate (plan.hpp): per pivot column, -2 if the pivot was the column's
+    // diagonal candidate (KLU keeps track of which row "is the diagonal" as off-diagonal pivots
+    // exchange the roles: klu_kernel's P / Pinv flips), else the pivot-order row of the diagonal
+    // candidate that failed the threshold test, or -1 if it was pivotal already
+    std::vector<int> diag_cand;
     int status = KLU_OK;
 };
 

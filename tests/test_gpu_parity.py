@@ -555,7 +555,7 @@ def test_systems_that_need_other_pivots_are_reseeded(K, oracle, regime, monkeypa
     with K.analyze(Ai, Aj, n) as sym:
         raw = np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym, check=False))
         st, gr = (np_(t).copy() for t in K.last_status())
-        assert st.tolist() == [0, 0, 0, 0, 1, 0] and gr[2] > 1e6
+        assert st.tolist() == [0, 0, 2, 0, 1, 0] and gr[2] > 1e6   # 2: pivot-parity certificate failed
         x = np_(K.solve_with_symbol(Ai, Aj, Ax, b, sym))          # check=True: re-seeds 2 and 4
         st2, gr2 = (np_(t) for t in K.last_status())
         assert st2.tolist() == [0] * L and gr2.max() <= 1000.0 * (1 + 1e-9)

@@ -12,7 +12,7 @@ from klujax_b200 import synth
 
 def test_library_exports_every_declared_symbol(cabi):
     names = cabi.declared_symbols()
-    assert len(names) == 29
+    assert len(names) >= 49  # 29 of round 1 + _ex, _dev, reseed, selftest entries (round 2)
     lib = cabi.lib()
     for nm in names:
         assert hasattr(lib, nm), nm
