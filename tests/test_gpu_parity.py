@@ -292,7 +292,7 @@ def test_level_regime_on_small_cases(K, oracle, dtype, monkeypatch):
 
 
 # ------------------------------------------------------------------ full-size properties
-def test_cfg5_full_size_properties(K):
+def test_cfg5_full_size_properties(K, oracle):
     """n_lhs = 65536, n_col = 128, complex128: too big for the oracle in seconds, so
     check size-independent properties: residual on every system, linearity, status."""
     import torch
@@ -312,6 +312,13 @@ def test_cfg5_full_size_properties(K):
     res = (torch.linalg.vector_norm(Ax_x - b, dim=1) / torch.linalg.vector_norm(b, dim=1)).max()
     assert float(res) < RES_TOL
     assert float((x2 - 3.0 * x).abs().max() / x.abs().max()) < 1e-13
+    # a sample of the full batch against the oracle (per-system klu_factor + klu_solve)
+    idx = np.unique(np.linspace(0, L - 1, 384).astype(int))
+    ti = torch.from_numpy(idx).cuda()
+    so = oracle.analyze(pat.Ai, pat.Aj, n)
+    ref = oracle.solve_with_symbol(pat.Ai, pat.Aj, np_(Ax[ti]), np_(b[ti]), so)
+    oracle.free_symbolic(so)
+    assert relerr(np_(x[ti]), ref) < X_TOL
 
 
 # ------------------------------------------------------------------ dot (next: f1)
@@ -569,7 +576,7 @@ def test_systems_that_need_other_pivots_are_reseeded(K, oracle, regime, monkeypa
 
 
 @pytest.mark.gpu
-def test_cfg4_full_size_properties(K):
+def test_cfg4_full_size_properties(K, oracle):
     """BASELINE.json config 4 at full size (n = 20 000, 128 systems, planted BTF): refactor +
     solve + transpose solve, checked through size-independent properties (residuals of every
     system through the COO product, status, growth certificate, solve/tsolve adjointness)."""
@@ -594,6 +601,15 @@ def test_cfg4_full_size_properties(K):
     # <A^-T c, b> == <c, A^-1 b>
     lhs, rhs = (y * b).sum((1, 2)), (c * x).sum((1, 2))
     assert float(((lhs - rhs).abs() / (lhs.abs() + rhs.abs() + 1e-300)).max()) < 1e-9
+    # a sample of the batch against the oracle: klu_factor at t = 0, klu_refactor at t = 3, solves
+    idx = [0, 41, 86, 127]
+    so = oracle.analyze(pat.Ai, pat.Aj, n)
+    no = oracle.factor(pat.Ai, pat.Aj, pat.values(0, L)[idx], so)
+    no = oracle.refactor(pat.Ai, pat.Aj, np_(Ax)[idx], so, no)
+    assert relerr(np_(x)[idx], oracle.solve_with_numeric(so, no, np_(b)[idx])) < X_TOL
+    assert relerr(np_(y)[idx], oracle.solve_with_numeric(so, no, np_(c)[idx], transpose=True)) < X_TOL
+    oracle.free_numeric(no)
+    oracle.free_symbolic(so)
 
 
 @pytest.mark.gpu
@@ -616,6 +632,64 @@ def test_cfg3_full_grid_properties(K):
     res = torch.linalg.vector_norm(K.dot(Ai, Aj, Ax, x) - b, dim=1) / torch.linalg.vector_norm(b, dim=1)
     assert float(res.max()) < RES_TOL
     assert float((x2 - (x[:, :, :1] - 2.0 * x[:, :, 1:2])).abs().max() / x.abs().max()) < 1e-12
+
+
+@pytest.mark.gpu
+def test_cfg3_full_rhs_width_vs_oracle(K, oracle):
+    """Config 3 at its full matrix size and right-hand-side width (256 x 256 grid, n_rhs = 256),
+    two systems: factor once, solve_with_numeric, x against the oracle at 1e-10."""
+    import torch
+    g, L, r = 256, 2, 256
+    Ai_h, Aj_h, Ax_h = synth.poisson2d(g, L)
+    n = g * g
+    b_h = np.random.default_rng(3).standard_normal((L, n, r))
+    so = oracle.analyze(Ai_h, Aj_h, n)
+    no = oracle.factor(Ai_h, Aj_h, Ax_h, so)
+    ref = oracle.solve_with_numeric(so, no, b_h)
+    oracle.free_numeric(no)
+    oracle.free_symbolic(so)
+    with K.analyze(Ai_h, Aj_h, n) as sym, K.factor(Ai_h, Aj_h, Ax_h, sym) as num:
+        x = np_(K.solve_with_numeric(num, torch.from_numpy(b_h).cuda(), sym))
+    assert relerr(x, ref) < X_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("r", [1, 4])
+def test_cfg2_full_batch_vs_oracle(K, oracle, r):
+    """Config 2 at its full batch (n_col = 64, n_lhs = 4096), one and four right-hand sides:
+    every system against the oracle."""
+    n, L = 64, 4096
+    pat = synth.SaxPattern(n, seed=1)
+    Ax = pat.values_fast(L, seed=4)
+    rng = np.random.default_rng(6)
+    b = rng.standard_normal((L, n, r)) + 1j * rng.standard_normal((L, n, r))
+    so = oracle.analyze(pat.Ai, pat.Aj, n)
+    ref = oracle.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, so)
+    reft = oracle.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, so, transpose=True)
+    oracle.free_symbolic(so)
+    with K.analyze(pat.Ai, pat.Aj, n) as sym:
+        assert relerr(np_(K.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, sym)), ref) < X_TOL
+        assert relerr(np_(K.tsolve_with_symbol(pat.Ai, pat.Aj, Ax, b, sym)), reft) < X_TOL
+
+
+@pytest.mark.gpu
+def test_rowreg_kernel_matches_the_shared_memory_kernels(K, oracle, monkeypatch):
+    """The register-resident kernel (opt-in, generated PTX + driver JIT) on the cfg 2 shape."""
+    n, L = 64, 512
+    pat = synth.SaxPattern(n, seed=1)
+    Ax = pat.values_fast(L, seed=8)
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal((L, n, 2)) + 1j * rng.standard_normal((L, n, 2))
+    so = oracle.analyze(pat.Ai, pat.Aj, n)
+    ref = oracle.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, so)
+    oracle.free_symbolic(so)
+    monkeypatch.setenv("KLUJAX_CUDA_ROWREG", "1")
+    monkeypatch.setenv("KLUJAX_CUDA_ROWREG_REQUIRE", "1")
+    with K.analyze(pat.Ai, pat.Aj, n) as sym:
+        x = np_(K.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, sym))
+        st, gr = K.last_status()
+        assert int(st.abs().max()) == 0 and float(gr.max()) <= 1000.0
+    assert relerr(x, ref) < X_TOL
 
 
 @pytest.mark.gpu
