@@ -310,6 +310,10 @@ int klujax_cuda_rowreg_selftest(uint64_t symbolic, int is_complex, int transpose
                                 int32_t* status_out, double* growth_out, int64_t* stats16,
                                 const char* ptx_path);
 
+/* 1 if the library was built with the XLA-FFI handlers of klujax_b200/csrc/klujax_cuda_ffi.cc
+ * (xla/ffi/api/ffi.h on the include path), 0 if that file compiled to its stub. */
+int klujax_cuda_ffi_available(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 OUT = os.path.join(OUT_DIR, "libklujax_cuda.so")
-SOURCES = ["klujax_cuda.cu", "ordering.cpp", "seed_lu.cpp", "plan.cpp", "rowreg.cpp", "rowreg_ptx.cpp"]
+SOURCES = ["klujax_cuda.cu", "ordering.cpp", "seed_lu.cpp", "plan.cpp", "rowreg.cpp", "rowreg_ptx.cpp",
+           "klujax_cuda_ffi.cc"]  # the FFI shim compiles to a stub where the XLA headers are absent
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".hpp", ".cuh", ".h"))) + \
           [os.path.join("..", "..", "include", "klujax_cuda.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
