@@ -14,8 +14,14 @@ _API = ("solve", "dot", "dot_transpose_ax", "solve_with_symbol_value_and_jvp",
         "free_symbolic", "free_numeric", "KLUHandleManager", "KlujaxCudaError", "last_status")
 
 
+_SHARD = ("analyze_sharded", "solve_with_symbol_sharded", "ShardedSymbolic", "shard_range", "gather_sharded")
+
+
 def __getattr__(name):  # lazy: `import klujax_b200.synth` must not need torch
     if name in _API:
         from . import api
         return getattr(api, name)
+    if name in _SHARD:
+        from . import shard
+        return getattr(shard, name)
     raise AttributeError(name)

@@ -109,6 +109,7 @@ struct Seeded {
 struct Symbolic {
     CscPattern A;
     Ordering ord;
+    int device = -1;  // CUDA device that holds the schedules (set by the first numeric call)
     std::vector<int> Ai, Aj;  // COO of the analyze call
     Seeded seeded[2];
     // per-stream scratch of the COO map (slot of every COO entry of the call + pattern flag):
@@ -136,16 +137,17 @@ struct NumericBatch {
 static std::mutex g_reg_mu;
 static std::unordered_map<uint32_t, NumericBatch*> g_batches;
 static uint32_t g_next_batch = 1;
-static int g_num_sms = 0;
+static int g_num_sms[64] = {0};
 
 static int num_sms() {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!g_num_sms[dev]) {
+        cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms[dev] <= 0) g_num_sms[dev] = 148;
     }
-    return g_num_sms;
+    return g_num_sms[dev];
 }
 
 static inline Symbolic* sym_of(uint64_t h) { return reinterpret_cast<Symbolic*>(static_cast<uintptr_t>(h)); }
@@ -640,6 +642,16 @@ static int launch_rowreg(Symbolic* S, int cx, RRKernel* K, const Op& op) {
 
 static int run_numeric(Symbolic* S, int cx, const Op& op) {
     std::lock_guard<std::mutex> lock(S->mu);
+    {
+        // the device copies of the schedule live on ONE device: a handle is bound to the device of
+        // its first numeric call (one process driving several GPUs analyzes once per device)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (S->device < 0) S->device = dev;
+        if (S->device != dev)
+            return fail(KLU_INVALID, "symbolic handle belongs to CUDA device " + std::to_string(S->device) +
+                                         ", the call runs on device " + std::to_string(dev));
+    }
     Seeded& sd = S->seeded[cx];
     const bool factor = op.mode <= PM_FACTOR_TSOLVE;
     if (op.L <= 0) return 0;
@@ -654,6 +666,7 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
         }
         S->cur = slot.get();
     }
+    if (factor && op.nz <= 0) return fail(KLU_SINGULAR, "matrix without entries is singular");
     if (factor) {
         int e = ensure_seeded_dev(S, cx, op.nz, op.Ai, op.Aj, op.Ax, op.st);
         if (e) return e;
@@ -1228,11 +1241,12 @@ DEF_SWS_EX(klujax_cuda_tsolve_with_symbol_ex_c128, 1, 1)
 // object like klujax.cpp:336 does after every call.
 namespace {
 struct SolveCacheEntry {
-    int n = 0;
+    int n = 0, device = 0;  // the device copies of (Ai, Aj) and of the schedule live on ONE device
     std::vector<int32_t> Ai, Aj;
     uint64_t sym = 0;
     DevBuf dAi, dAj;
     uint64_t stamp = 0;
+    int users = 0;  // calls in flight outside the mutex: such an entry is not evicted
 };
 std::mutex g_solve_cache_mu;
 std::vector<std::unique_ptr<SolveCacheEntry>> g_solve_cache;
@@ -1245,10 +1259,14 @@ static int do_solve(int cx, int n_lhs, int n_col, int n_rhs, int n_nz, const int
                     int32_t* status, double* growth, void* stream) {
     if (n_nz < 0 || (n_nz > 0 && (!Ai_host || !Aj_host))) return fail(KLU_INVALID, "solve: null indices");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    std::lock_guard<std::mutex> lock(g_solve_cache_mu);
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    // the mutex covers the lookup / insertion / eviction only; the numeric call runs outside it, so
+    // solve() calls on different patterns or devices do not serialise each other
+    std::unique_lock<std::mutex> lock(g_solve_cache_mu);
     SolveCacheEntry* hit = nullptr;
     for (auto& e : g_solve_cache)
-        if (e->n == n_col && static_cast<int>(e->Ai.size()) == n_nz &&
+        if (e->n == n_col && e->device == cur_dev && static_cast<int>(e->Ai.size()) == n_nz &&
             std::equal(e->Ai.begin(), e->Ai.end(), Ai_host) && std::equal(e->Aj.begin(), e->Aj.end(), Aj_host)) {
             hit = e.get();
             break;
@@ -1258,6 +1276,7 @@ static int do_solve(int cx, int n_lhs, int n_col, int n_rhs, int n_nz, const int
         int rc = klujax_cuda_analyze(n_col, n_nz, Ai_host, Aj_host, &ne->sym);
         if (rc) return rc;
         ne->n = n_col;
+        ne->device = cur_dev;
         ne->Ai.assign(Ai_host, Ai_host + n_nz);
         ne->Aj.assign(Aj_host, Aj_host + n_nz);
         cudaError_t e = ne->dAi.alloc(sizeof(int) * (n_nz + 1));
@@ -1271,18 +1290,27 @@ static int do_solve(int cx, int n_lhs, int n_col, int n_rhs, int n_nz, const int
         if (g_solve_cache.size() >= kSolveCacheEntries) {  // evict the least recently used pattern
             size_t victim = 0;
             for (size_t i = 1; i < g_solve_cache.size(); ++i)
-                if (g_solve_cache[i]->stamp < g_solve_cache[victim]->stamp) victim = i;
-            cudaDeviceSynchronize();  // its kernels may still be in flight on another stream
-            klujax_cuda_free_symbolic(g_solve_cache[victim]->sym, nullptr);
-            g_solve_cache.erase(g_solve_cache.begin() + victim);
+                if (g_solve_cache[i]->users == 0 &&
+                    (g_solve_cache[victim]->users > 0 || g_solve_cache[i]->stamp < g_solve_cache[victim]->stamp))
+                    victim = i;
+            if (g_solve_cache[victim]->users == 0) {
+                cudaDeviceSynchronize();  // its kernels may still be in flight on another stream
+                klujax_cuda_free_symbolic(g_solve_cache[victim]->sym, nullptr);
+                g_solve_cache.erase(g_solve_cache.begin() + victim);
+            }
         }
         g_solve_cache.push_back(std::move(ne));
         hit = g_solve_cache.back().get();
     }
     hit->stamp = ++g_solve_stamp;
-    int rc = do_solve_with_symbol(cx, 0, hit->sym, n_lhs, n_col, n_rhs, n_nz, hit->dAi.as<int32_t>(),
-                                  hit->dAj.as<int32_t>(), Ax, b, x, status, growth, stream);
-    if (rc) {  // a failed call (singular seed, ...) leaves nothing behind, like the reference
+    hit->users++;
+    const uint64_t hsym = hit->sym;
+    const int32_t *dAi = hit->dAi.as<int32_t>(), *dAj = hit->dAj.as<int32_t>();
+    lock.unlock();
+    int rc = do_solve_with_symbol(cx, 0, hsym, n_lhs, n_col, n_rhs, n_nz, dAi, dAj, Ax, b, x, status, growth, stream);
+    lock.lock();
+    hit->users--;
+    if (rc && hit->users == 0) {  // a failed call (singular seed, ...) leaves nothing behind, like the reference
         cudaStreamSynchronize(st);
         for (size_t i = 0; i < g_solve_cache.size(); ++i)
             if (g_solve_cache[i].get() == hit) {

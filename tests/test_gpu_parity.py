@@ -783,3 +783,33 @@ def test_fuzz_structures_all_kernels(K, oracle, monkeypatch):
                 assert relerr(x, ref) < tol and relerr(x, true) < tol, (kind, n, dtype, wide)
                 assert relerr(xt, reft) < tolt and relerr(xt, truet) < tolt, (kind, n, dtype, wide)
                 assert relerr(xn, ref) < tol, (kind, n, dtype, wide)
+
+
+@pytest.mark.gpu
+def test_one_process_sharded_over_the_visible_gpus(K, oracle):
+    """solve_with_symbol_sharded: the n_lhs batch cut into contiguous blocks over every visible
+    GPU, one process, replicated symbolic handles, no data-path collective (the reference's only
+    multi-device test is /root/reference/tests.py:472-492).  With one GPU it degenerates to one
+    shard; with several the blocks run concurrently."""
+    import torch
+    n, L = 64, 1031  # ragged over any device count
+    pat = synth.SaxPattern(n, seed=1)
+    Ax = pat.values_fast(L, seed=3)
+    rng = np.random.default_rng(4)
+    b = rng.standard_normal((L, n, 2)) + 1j * rng.standard_normal((L, n, 2))
+    so = oracle.analyze(pat.Ai, pat.Aj, n)
+    ref = oracle.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, so)
+    oracle.free_symbolic(so)
+    devs = list(range(torch.cuda.device_count()))
+    with K.analyze_sharded(pat.Ai, pat.Aj, n, devs) as ssym:
+        x = K.solve_with_symbol_sharded(pat.Ai, pat.Aj, torch.from_numpy(Ax).pin_memory(),
+                                        torch.from_numpy(b).pin_memory(), ssym)
+        assert relerr(x.numpy(), ref) < X_TOL
+        parts = K.solve_with_symbol_sharded(pat.Ai, pat.Aj, Ax, b, ssym, gather=False)
+        assert len(parts) == len(devs) and sum(p.shape[0] for p in parts if p is not None) == L
+        if len(devs) > 1:
+            assert {p.device.index for p in parts if p is not None} == set(devs)
+            # a handle is bound to its device
+            with torch.cuda.device(devs[1]):
+                with pytest.raises(K.KlujaxCudaError):
+                    K.solve_with_symbol(pat.Ai, pat.Aj, Ax[:4], b[:4], ssym.handles[0])
