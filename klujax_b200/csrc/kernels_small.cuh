@@ -42,6 +42,7 @@ struct Sc<double> {
         return __shfl_down_sync(0xffffffffu, a, o, w);
     }
     __device__ static __forceinline__ V one() { return 1.0; }
+    __device__ static __forceinline__ V shfl_idx(V a, int src) { return __shfl_sync(0xffffffffu, a, src); }
     // split accumulators: independent FMA chains, combined once per batch
     struct Acc {
         double p, q;
@@ -104,6 +105,9 @@ struct Sc<zc> {
                             __shfl_down_sync(0xffffffffu, a.y, o, w));
     }
     __device__ static __forceinline__ V one() { return make_double2(1.0, 0.0); }
+    __device__ static __forceinline__ V shfl_idx(V a, int src) {
+        return make_double2(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src));
+    }
     // four independent FMA chains (xx, yy, xy, yx), combined once per batch
     struct Acc {
         double xx, yy, xy, yx;
@@ -138,6 +142,8 @@ struct SmallArgs {
     uint16_t chunk_ptr[2][kMaxChunks + 1];  // first batch of each chunk
     int W;                   // systems (= consumer warps) per CTA
     int n, n_val, n_slots, zero_slot, rc, nz, flags;
+    const uint16_t* tail_tab;  // dense tail in registers (kernels_wide.cuh): slots of the tail block, or null
+    int tail_t0;
     const int* coo_dst;      // [nz] slot of each COO entry of this call, -1 = not in pattern
     const int* remap;        // compacted programs (plan.hpp: TaskProgram::remap): layout slot -> slot, else null
     const int* pattern_bad;  // device flag set by the COO map

@@ -33,8 +33,114 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dense tail in registers.  The last kTail = 32 pivots of the big block form a (nearly) dense
+// trailing submatrix that carries ~60 % of the multiply-adds of the SAX systems (cfg 5: 10.4 k of
+// 17.4 k) and the longest dependent chain (one pivot after the other).  Interpreted, every one of
+// those multiply-adds costs three 16-byte shared-memory loads, one store and a schedule word.
+// Here the four warps of the system take the Schur complement the interpreted steps left in
+// shared memory into registers - warp w owns columns 8w..8w+7, lane i owns row i - and eliminate
+// in lock step: the pivot row reaches the lanes of a warp by SHFL.IDX (its entries sit in lane k of
+// the same warp), the multipliers L(:,k) of the warp that owns column k reach the other three
+// through a 512-byte double-buffered exchange in shared memory (one named barrier per pivot);
+// lanes at or above the pivot row multiply by zero instead of being predicated off.  The
+// right-hand side rides along as a 33rd column (warp 0), U and the reciprocal pivots go back to
+// their slots, warp 0 does the back substitution of the 32 tail rows by columns (x(j) by shuffle,
+// U(:,j) from its slots) and leaves x in the right-hand-side slots for the interpreted back
+// substitution of the rows above.  The loop over the pivots is 4 (owner warp) x 8 (unrolled
+// column): ~1.5 k instructions, resident in the instruction cache (unlike the straight-line
+// kernels of rowreg.cpp, profiles/rowreg_r02.md).
+// Replaces, for those pivots, the column loop of klu_refactor and the tail of klu_solve's
+// L- and U-solves (/root/reference/klujax.cpp:441-445 through KLU).
+// The packer starts a new schedule chunk at the stage, so that it is entered from the chunk loop and
+// not from the step loop, and the stage is a real function with its own register frame (inlined
+// into the step loop its registers pushed the interpreter into spills: 4.9 -> 7.5 ms).  The loop
+// over the 32 pivots is NOT unrolled and has no warp-specific code paths (a first version unrolled
+// per owner warp and column: 10 k instructions, fetch-bound like the straight-line kernels):
+// columns at or left of the pivot multiply by zero, warps whose columns are all done skip the step.
+struct TailResult {
+    double gmax;
+    int bad;
+};
 template <typename T>
-__global__ void __launch_bounds__(32 * (kWarpsPerSystem * kMaxWideSystems + 1), 1)
+__device__ __forceinline__ TailResult tail_stage(const uint16_t* __restrict__ tab, unsigned char* Vb, double* Rs,
+                                              typename Sc<T>::V* Xs, int wq, int lane, int bar_id) {
+    using S = Sc<T>;
+    using V_t = typename S::V;
+    V_t* V = reinterpret_cast<V_t*>(Vb);
+    TailResult res{0.0, 0};
+    V_t acol[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const uint32_t s = __ldg(tab + (wq * 8 + jj) * kTail + lane);
+        acol[jj] = s != 0xFFFFu ? V[s] : S::zero();
+    }
+    V_t y = wq == 0 ? Xs[0] : S::zero();
+    V_t* lbuf = reinterpret_cast<V_t*>(Rs);  // Rs is dead after the right-hand side was loaded (solve mode)
+#pragma unroll 1
+    for (int k = 0; k < kTail; ++k) {
+        const int kb = k >> 3, c = k & 7;
+        V_t l = S::zero();
+        if (wq == kb) {  // the warp that owns column k: pivot, multipliers, certificate
+            V_t ac = acol[0];
+#pragma unroll
+            for (int jj = 1; jj < 8; ++jj)
+                if (c == jj) ac = acol[jj];
+            const V_t d = S::shfl_idx(ac, k);
+            res.bad |= S::bad_pivot(d) ? 1 : 0;
+            const V_t inv = S::fast_recip(d);
+            if (lane > k) l = S::mul(ac, inv);
+            res.gmax = fmax(res.gmax, S::mag2(l));
+            if (lane == k) {  // the diagonal slot holds the reciprocal pivot
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)
+                    if (c == jj) acol[jj] = inv;
+            }
+            lbuf[(k & 1) * kTail + lane] = l;
+        }
+        named_barrier(bar_id, kLanesPerSystem);
+        if (wq * 8 + 7 > k || wq == 0) {  // warps whose columns are all at or left of the pivot are done
+            if (wq != kb) l = lbuf[(k & 1) * kTail + lane];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const V_t u = S::shfl_idx(acol[jj], k);
+                V_t lj = l;
+                if (wq * 8 + jj <= k) lj = S::zero();  // finished column: multiply by zero
+                S::fms_acc(acol[jj], lj, u);
+            }
+            if (wq == 0) S::fms_acc(y, l, S::shfl_idx(y, k));  // forward solve, fused
+        }
+    }
+    // U and the reciprocal pivots back to their slots (rows at or above the diagonal)
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const uint32_t s = __ldg(tab + (wq * 8 + jj) * kTail + lane);
+        if (s != 0xFFFFu && lane <= wq * 8 + jj) V[s] = acol[jj];
+    }
+    named_barrier(bar_id, kLanesPerSystem);
+    if (wq == 0) {  // back substitution of the tail rows, by columns
+        const V_t inv_me = V[__ldg(tab + lane * kTail + lane)];
+#pragma unroll 1
+        for (int j = kTail - 1; j >= 0; --j) {
+            const V_t t = S::mul(y, inv_me);
+            const V_t xj = S::shfl_idx(t, j);
+            if (lane == j) y = t;
+            const uint32_t s = __ldg(tab + j * kTail + lane);
+            if (lane < j && s != 0xFFFFu) S::fms_acc(y, V[s], xj);
+        }
+        Xs[0] = y;
+    }
+    named_barrier(bar_id, kLanesPerSystem);
+    return res;
+}
+
+// TAIL = true: the variant with the register stage of the dense tail; it runs four systems per CTA
+// (17 warps, 5 per SM sub-partition: up to 96 registers per thread) instead of six (25 warps, 7 per
+// sub-partition: 72 registers): the stage holds 8 complex columns per lane, and in the 72-register
+// kernel it spilled into the interpreter loop.  Opt-in (KLUJAX_CUDA_TAIL=1), see klujax_cuda.cu.
+constexpr int kMaxWideSystemsTail = 4;
+template <typename T, bool TAIL>
+__global__ void __launch_bounds__(32 * (kWarpsPerSystem * (TAIL ? kMaxWideSystemsTail : kMaxWideSystems) + 1), 1)
     wide_kernel(const __grid_constant__ SmallArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
@@ -193,6 +299,12 @@ __global__ void __launch_bounds__(32 * (kWarpsPerSystem * kMaxWideSystems + 1), 
                 const uint2* p = reinterpret_cast<const uint2*>(ring + buf * kChunkBytes) + tid;
                 const int s0 = a.chunk_ptr[pi][c], s1 = a.chunk_ptr[pi][c + 1];
                 uint32_t cw = a.ctrl[pi][s0];
+                if (TAIL && (cw & 32u)) {  // first step of a chunk, after a level end: the dense tail in registers
+                    const TailResult tr = tail_stage<T>(a.tail_tab, Vb, Rs, V + a.n_val + (a.tail_t0 + lane) * a.rc, wq,
+                                                        lane, bar_id);
+                    bad |= tr.bad != 0;
+                    gmax = fmax(gmax, tr.gmax);
+                }
                 for (int s = s0; s < s1; ++s) {
                     const bool level_end = (cw & 16u) != 0;
                     const uint2 hw = p[0];

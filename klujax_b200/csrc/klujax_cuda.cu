@@ -70,6 +70,8 @@ struct DevBuf {
 
 struct SmallProg {
     DevBuf stream, remap, rs_slot;  // remap / rs_slot: compacted programs only
+    DevBuf tail_tab;                // register stage of the dense tail (plan.hpp), if the program uses it
+    int tail_t0 = -1;
     std::vector<uint32_t> ctrl;
     std::vector<uint16_t> chunk_ptr;
     int nchunks = 0, nbatch = 0, n_slots = 0, zero_slot = 0, nlevels = 0, n_val = 0;
@@ -265,9 +267,10 @@ static int ensure_seeded_dev(Symbolic* S, int cx, int nz, const int32_t* Ai_dev,
 // ---------------------------------------------------------------------------
 // program caches
 // ---------------------------------------------------------------------------
-static int get_small_prog(Symbolic* S, int cx, int mode, int rc, bool wide, bool compact, SmallProg** out) {
+static int get_small_prog(Symbolic* S, int cx, int mode, int rc, bool wide, bool compact, SmallProg** out,
+                          bool tail = false) {
     Seeded& sd = S->seeded[cx];
-    auto key = std::make_pair(mode, rc + (wide ? 1000 : 0) + (compact ? 100000 : 0));
+    auto key = std::make_pair(mode, rc + (wide ? 1000 : 0) + (compact ? 100000 : 0) + (tail ? 10000000 : 0));
     auto it = sd.small.find(key);
     if (it == sd.small.end()) {
         TaskProgram tp;
@@ -278,7 +281,8 @@ static int get_small_prog(Symbolic* S, int cx, int mode, int rc, bool wide, bool
             split = 111;  // one multiply-add per partial update (measured best: 11 < 14 < 24 < 47;
                           // the kernel's step format is fixed to it)
         }
-        build_program(S->ord, sd.piv, sd.lay, mode, rc, tp, split, compact ? (cx ? 8 : 16) : 0);
+        const int tail_t0 = (tail && wide) ? pick_tail(S->ord, sd.piv, sd.lay) : -1;
+        build_program(S->ord, sd.piv, sd.lay, mode, rc, tp, split, compact ? (cx ? 8 : 16) : 0, tail_t0);
         if (!(wide ? pack_program_wide(sd.lay, tp, pp, cx ? 16 : 8) : pack_program(sd.lay, tp, pp))) return fail(KLU_TOO_LARGE, "program does not fit the shared-memory regime");
         auto sp = std::make_unique<SmallProg>();
         CUDA_OK(sp->stream.upload(pp.stream));
@@ -291,6 +295,14 @@ static int get_small_prog(Symbolic* S, int cx, int mode, int rc, bool wide, bool
         sp->nlevels = tp.nlevels;
         sp->n_mac = tp.n_mac;
         sp->n_val = tp.n_val;
+        if (std::getenv("KLUJAX_CUDA_VERBOSE"))
+            std::fprintf(stderr, "[program] mode %d rc %d wide %d compact %d tail_t0 %d: %d steps/batches, %d levels (stage at %d), %lld multiply-adds, %d value slots, %d chunks\n",
+                         mode, rc, int(wide), int(compact), tp.tail_t0, pp.nbatch, tp.nlevels, tp.tail_level,
+                         static_cast<long long>(tp.n_mac), tp.n_val, pp.nchunks);
+        if (tp.tail_t0 >= 0) {
+            CUDA_OK(sp->tail_tab.upload(tp.tail_tab));
+            sp->tail_t0 = tp.tail_t0;
+        }
         if (!tp.remap.empty()) {
             CUDA_OK(sp->remap.upload(tp.remap));
             std::vector<int> rs(sd.lay.rs_slot.size());
@@ -392,7 +404,13 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     // (plan.hpp: TaskProgram::remap), so more systems fit in shared memory.
     bool compact = wide && factor && solve && !op.store_numeric && op.r <= rc;
     if (const char* ev = std::getenv("KLUJAX_CUDA_COMPACT")) compact = compact && std::atoi(ev) != 0;
-    int e = get_small_prog(S, cx, op.mode, rc, wide, compact, &p0);
+    // dense tail in registers (kernels_wide.cuh): fused factor + solve with one right-hand side.
+    // An experiment, OFF unless KLUJAX_CUDA_TAIL=1: it halves the interpreted steps of config 5 but
+    // runs 7.4 ms against the interpreter's 4.97 ms (profiles/tail_stage_r02.md).
+    bool tail = false;
+    if (const char* ev = std::getenv("KLUJAX_CUDA_TAIL"))
+        tail = std::atoi(ev) != 0 && wide && op.mode == PM_FACTOR_SOLVE && !op.store_numeric && rc == 1 && op.r == 1;
+    int e = get_small_prog(S, cx, op.mode, rc, wide, compact, &p0, tail);
     if (!e && solve && op.r > rc) e = get_small_prog(S, cx, transpose ? PM_TSOLVE : PM_SOLVE, rc, wide, false, &p1);
     if (e == KLU_TOO_LARGE && wide) {
         // the single-multiply-add schedule of the multi-warp kernel has too many steps for the
@@ -431,6 +449,8 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     a.pattern_bad = S->cur->bad.as<int>();
     a.rs_ptr = sd.d_rs_ptr.as<int>();
     a.rs_slot = p0->rs_slot.p ? p0->rs_slot.as<int>() : sd.d_rs_slot.as<int>();
+    a.tail_tab = p0->tail_t0 >= 0 ? p0->tail_tab.as<uint16_t>() : nullptr;
+    a.tail_t0 = p0->tail_t0;
     a.remap = p0->remap.p ? p0->remap.as<int>() : nullptr;
     a.in_perm = transpose ? sd.d_q.as<int>() : sd.d_pnum.as<int>();
     a.out_perm = transpose ? sd.d_pnum.as<int>() : sd.d_q.as<int>();
@@ -453,7 +473,9 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     // at most 5 systems per CTA (thread limit), several CTAs per SM when systems are small.
     const size_t per_sys = wide ? ((static_cast<size_t>(a.n_slots) * vsz + n * 8ull + 16 + 15) & ~size_t(15))
                                 : ((static_cast<size_t>(a.n_slots) * vsz + n * 8ull + 15) & ~size_t(15));
-    int W = static_cast<int>(std::min<size_t>(wide ? kMaxWideSystems : 16, (kMaxDynSmem - kSmallHeaderBytes) / per_sys));
+    const bool tail_kernel = wide && p0->tail_t0 >= 0;
+    int W = static_cast<int>(std::min<size_t>(wide ? (tail_kernel ? kMaxWideSystemsTail : kMaxWideSystems) : 16,
+                                              (kMaxDynSmem - kSmallHeaderBytes) / per_sys));
     if (W < 1) return fail(KLU_TOO_LARGE, "system does not fit the shared-memory regime");
     const int sms = num_sms();
     while (W > 1 && (op.L + W - 1) / W < sms) --W;  // small batches: spread over all SMs first
@@ -461,7 +483,7 @@ static int launch_small(Symbolic* S, int cx, const Op& op) {
     a.W = W;
     const size_t smem = kSmallHeaderBytes + per_sys * W;
     const int threads = wide ? 32 * (kWarpsPerSystem * W + 1) : 32 * (W + 1);
-    auto kern = wide ? wide_kernel<T> : small_kernel<T>;
+    auto kern = wide ? (tail_kernel ? wide_kernel<T, true> : wide_kernel<T, false>) : small_kernel<T>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int occ = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));

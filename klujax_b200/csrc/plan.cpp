@@ -299,6 +299,7 @@ void rebalance_levels(TaskProgram& prog, int n_val, int lanes) {
 // Linear-scan slot allocation over the level sets (see TaskProgram::remap).
 void compact_slots(const SlotLayout& lay, TaskProgram& prog, int bank_cols) {
     const int nv = lay.n_val, nl = prog.nlevels;
+    auto in_tail = [&](int k) { return prog.tail_t0 >= 0 && k >= prog.tail_t0 && k < prog.tail_t0 + kTail; };
     const int NEVER = 1 << 30;
     std::vector<int> birth(nv, NEVER), death(nv, 0), first_write(nv, -1);
     for (int s = 0; s < nv; ++s)
@@ -324,6 +325,9 @@ void compact_slots(const SlotLayout& lay, TaskProgram& prog, int bank_cols) {
     }
     for (int s = 0; s < nv; ++s)
         if (birth[s] == NEVER) birth[s] = 0;  // never touched by a task: only the load phase sees it
+    // entries of the dense tail are read (and their U part rewritten) by the register stage
+    for (int s = 0; s < lay.n_lu; ++s)
+        if (in_tail(lay.slot_row[s]) && in_tail(lay.slot_col[s])) death[s] = std::max(death[s], prog.tail_level);
     // slots by birth level; slots that die at level d are free again from level d + 1
     std::vector<std::vector<int>> born(nl + 2), dies(nl + 2);
     for (int s = 0; s < nv; ++s) {
@@ -374,10 +378,31 @@ void compact_slots(const SlotLayout& lay, TaskProgram& prog, int bank_cols) {
 
 }  // namespace
 
+int pick_tail(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay) {
+    // the largest block; its last kTail pivots
+    int best = -1, bsz = 0;
+    for (int b = 0; b < ord.nblocks; ++b)
+        if (ord.R[b + 1] - ord.R[b] > bsz) bsz = ord.R[b + 1] - ord.R[b], best = b;
+    if (best < 0 || bsz < kTail + 8 || lay.n < 128) return -1;
+    const int t0 = ord.R[best + 1] - kTail;
+    for (int k = t0; k < t0 + kTail; ++k)
+        if (!piv.diag_cand.empty() && piv.diag_cand[k] != -2) return -1;  // the stage certifies diagonal pivots only
+    long long inside = 0;
+    for (int s = 0; s < lay.n_lu; ++s)
+        if (lay.slot_row[s] >= t0 && lay.slot_row[s] < t0 + kTail && lay.slot_col[s] >= t0 && lay.slot_col[s] < t0 + kTail) ++inside;
+    if (inside * 10 < 6LL * kTail * kTail) return -1;  // not dense enough to pay for lock-step elimination
+    for (int k = t0; k < t0 + kTail; ++k)  // every diagonal entry of the tail has a slot (always true)
+        if (lay.diag_slot[k] < 0) return -1;
+    return t0;
+}
+
 void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
-                   int rc, TaskProgram& prog, int split, int compact) {
+                   int rc, TaskProgram& prog, int split, int compact, int tail_t0) {
     const int n = lay.n;
     prog = TaskProgram();
+    if (mode != PM_FACTOR_SOLVE) tail_t0 = -1;
+    prog.tail_t0 = tail_t0;
+    auto in_tail = [&](int k) { return tail_t0 >= 0 && k >= tail_t0 && k < tail_t0 + kTail; };
     prog.mode = mode;
     prog.rc = rc;
     prog.n_val = lay.n_val;
@@ -414,6 +439,7 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
             dest.assign(ce - cb, {});
             for (int su = cb; su < dg; ++su) {
                 const int j = lay.slot_row[su];  // U(j,k)
+                if (in_tail(k) && in_tail(j)) continue;  // updates by tail pivots: register stage
                 for (int sl = lay.diag_slot[j] + 1; sl < lay.col_begin[j + 1]; ++sl) {
                     const int d = pos[lay.slot_row[sl]];  // (i,k) with L(i,j) != 0
                     dest[d - cb].emplace_back(sl, su);
@@ -421,6 +447,12 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
             }
             for (int s = cb; s < ce; ++s) {
                 const auto& pr = dest[s - cb];
+                if (in_tail(k) && in_tail(lay.slot_row[s])) {
+                    // entry of the dense tail: only the Schur-complement part; pivot, L scaling and
+                    // the certificate happen in the register stage
+                    if (!pr.empty()) lv.add(TK_SUB, s, -1, pr);
+                    continue;
+                }
                 if (s < dg) {
                     if (!pr.empty()) lv.add(TK_SUB, s, -1, pr);
                 } else if (s == dg) {
@@ -467,12 +499,23 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
                 for (int c = 0; c < rc; ++c) {
                     pairs.clear();
                     for (auto& e : offrow[i]) pairs.emplace_back(e.first, xs(e.second, c));
-                    for (auto& e : lrow[i]) pairs.emplace_back(e.first, xs(e.second, c));
+                    for (auto& e : lrow[i])
+                        if (!(in_tail(i) && in_tail(e.second))) pairs.emplace_back(e.first, xs(e.second, c));
                     lv.add(TK_SUB, xs(i, c), -1, pairs);
                 }
             }
+            if (tail_t0 >= k1 && tail_t0 < k2) {
+                // everything the register stage reads is final below this level; what it writes
+                // (x of the tail rows) is final at it
+                int top = 0;
+                for (const Task& t : prog.tasks) top = std::max(top, t.level);
+                prog.tail_level = top + 1;
+                for (int i = tail_t0; i < tail_t0 + kTail; ++i)
+                    for (int c = 0; c < rc; ++c) lv.val_level[xs(i, c)] = prog.tail_level;
+            }
             for (int i = k2 - 1; i >= k1; --i)
                 for (int c = 0; c < rc; ++c) {
+                    if (in_tail(i)) continue;  // back substitution of the tail: register stage
                     pairs.clear();
                     for (auto& e : urow[i]) pairs.emplace_back(e.first, xs(e.second, c));
                     lv.add(TK_MUL, xs(i, c), lay.diag_slot[i], pairs);
@@ -509,6 +552,7 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
     // stable sort by level (longest dots first inside a level)
     int maxlvl = 0;
     for (const Task& t : prog.tasks) maxlvl = std::max(maxlvl, t.level);
+    if (tail_t0 >= 0) maxlvl = std::max(maxlvl, prog.tail_level);
     prog.nlevels = maxlvl;
     std::stable_sort(prog.tasks.begin(), prog.tasks.end(), [](const Task& a, const Task& b) {
         if (a.level != b.level) return a.level < b.level;
@@ -522,6 +566,15 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
         !(std::getenv("KLUJAX_CUDA_REBALANCE") && std::atoi(std::getenv("KLUJAX_CUDA_REBALANCE")) == 0))
         rebalance_levels(prog, lay.n_val, 128);
     if (compact && do_factor && (do_solve || do_tsolve)) compact_slots(lay, prog, compact);
+    if (tail_t0 >= 0) {
+        prog.tail_tab.assign(static_cast<size_t>(kTail) * kTail, 0xFFFF);
+        for (int s = 0; s < lay.n_lu; ++s)
+            if (in_tail(lay.slot_row[s]) && in_tail(lay.slot_col[s])) {
+                const int ps = prog.remap.empty() ? s : prog.remap[s];
+                prog.tail_tab[static_cast<size_t>(lay.slot_col[s] - tail_t0) * kTail + (lay.slot_row[s] - tail_t0)] =
+                    static_cast<uint16_t>(ps);
+            }
+    }
 }
 
 bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out) {
@@ -709,8 +762,19 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
         out.nchunks++;
     };
     std::vector<int> order;
+    bool tail_pending = prog.tail_t0 >= 0;
     for (int l = 0; l < prog.nlevels; ++l) {
         const int tb = prog.level_ptr[l], te = prog.level_ptr[l + 1];
+        if (tail_pending && l + 1 >= prog.tail_level && te == tb && l + 1 == prog.nlevels) {
+            // nothing left after the register stage: an idle step carries its flag
+            if (used > 0) open_chunk();
+            uint32_t* base = out.stream.data() + chunk_base + used;
+            for (int k = 0; k < LANES; ++k) base[2 * k] = 0u, base[2 * k + 1] = idle_op;
+            out.ctrl.push_back(1u | 16u | 32u);
+            used += LANES * 2;
+            tail_pending = false;
+            continue;
+        }
         order.resize(te - tb);
         for (int t = tb; t < te; ++t) order[t - tb] = t;  // already sorted by length, longest first
         if (bank_order) order_for_banks(prog, order, 128 / elem_bytes);
@@ -721,7 +785,9 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
                 if (prog.tasks[order[i + k]].plen > 1) return false;
             const int P = 1;
             const int words = LANES * (1 + P);
-            if (used + words > kChunkWords) open_chunk();
+            // the register stage is entered at a chunk boundary (kernels_wide.cuh)
+            const bool tail_here = tail_pending && l + 1 >= prog.tail_level;
+            if (used + words > kChunkWords || (tail_here && used > 0)) open_chunk();
             uint32_t* base = out.stream.data() + chunk_base + used;
             for (size_t k = 0; k < cnt; ++k) {
                 const Task& tk = prog.tasks[order[i + k]];
@@ -734,10 +800,22 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
                                           : idle_op;
             }
             const bool level_end = (i + LANES >= order.size());
-            out.ctrl.push_back(static_cast<uint32_t>(P) | (level_end ? 16u : 0u));
+            uint32_t cwv = static_cast<uint32_t>(P) | (level_end ? 16u : 0u);
+            if (tail_pending && l + 1 >= prog.tail_level) {  // the register stage runs before this step
+                cwv |= 32u;
+                tail_pending = false;
+            }
+            out.ctrl.push_back(cwv);
             used += words;
             out.lines_used += 1 + P;
         }
+    }
+    if (tail_pending) {  // no step at or after the stage's level: an idle step carries the flag
+        if (used > 0) open_chunk();
+        uint32_t* base = out.stream.data() + chunk_base + used;
+        for (int k = 0; k < LANES; ++k) base[2 * k] = 0u, base[2 * k + 1] = idle_op;
+        out.ctrl.push_back(1u | 16u | 32u);
+        used += LANES * 2;
     }
     out.chunk_ptr.push_back(static_cast<uint16_t>(out.ctrl.size()));
     out.nbatch = static_cast<int>(out.ctrl.size());

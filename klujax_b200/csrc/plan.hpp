@@ -85,13 +85,24 @@ struct TaskProgram {
     // (empty = identity, n_val = lay.n_val).
     int n_val = 0;
     std::vector<int> remap;
+    // Dense tail in registers (kernels_wide.cuh: tail stage).  The last kTail pivots of the
+    // largest block form a (nearly) dense trailing submatrix that holds most of the multiply-adds;
+    // with tail_t0 >= 0 the program leaves its factorization, its part of the forward solve and
+    // its back substitution to the kernel's register stage: tasks fed by tail pivots are dropped,
+    // the stage runs before the first step of level tail_level, tail_tab[col*kTail + row] is the
+    // (physical) slot of entry (tail_t0 + row, tail_t0 + col) or 0xFFFF.
+    int tail_t0 = -1, tail_level = 0;
+    std::vector<uint16_t> tail_tab;
 };
+constexpr int kTail = 32;
 
 void build_layout(const CscPattern& A, const Ordering& ord, const PivotPlan& piv, SlotLayout& lay);
 // compact: 0 = keep the layout's slots; else recycle dead slots (TaskProgram::remap), keeping
 // every slot in its shared-memory bank column modulo `compact` (8 for 16-byte, 16 for 8-byte values)
 void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, int mode,
-                   int rc, TaskProgram& prog, int split = 0, int compact = 0);
+                   int rc, TaskProgram& prog, int split = 0, int compact = 0, int tail_t0 = -1);
+// first pivot of a dense tail the register stage can take (fused factor + solve), or -1
+int pick_tail(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay);
 
 // Packed schedule of the shared-memory (small-matrix) regime: one warp per system.
 //

@@ -693,6 +693,32 @@ def test_rowreg_kernel_matches_the_shared_memory_kernels(K, oracle, monkeypatch)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_register_tail_stage_matches_the_interpreter(K, oracle, dtype, monkeypatch):
+    """The dense-tail register stage of the multi-warp kernel (opt-in, profiles/tail_stage_r02.md)
+    on the cfg 5 shape: same solution as the oracle and as the default interpreted schedule."""
+    n, L = 128, 300
+    pat = synth.SaxPattern(n, seed=2)
+    Ax = pat.values_fast(L, seed=7)
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal((L, n, 1)) + 1j * rng.standard_normal((L, n, 1))
+    if dtype == np.float64:
+        Ax, b = np.ascontiguousarray(Ax.real + Ax.imag), np.ascontiguousarray(b.real)
+    so = oracle.analyze(pat.Ai, pat.Aj, n)
+    ref = oracle.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, so)
+    oracle.free_symbolic(so)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("KLUJAX_CUDA_TAIL", mode)
+        with K.analyze(pat.Ai, pat.Aj, n) as sym:
+            out[mode] = np_(K.solve_with_symbol(pat.Ai, pat.Aj, Ax, b, sym))
+            st, gr = K.last_status()
+            assert int(st.abs().max()) == 0 and float(gr.max()) <= 1000.0
+        assert relerr(out[mode], ref) < X_TOL
+    assert relerr(out["1"], out["0"]) < X_TOL
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n", [256, 320])
 def test_large_shared_memory_systems(K, oracle, n):
     """Systems that fill most of an SM's shared memory (one or two resident systems): n = 256
