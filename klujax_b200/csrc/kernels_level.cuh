@@ -39,8 +39,11 @@ struct LevelProg {
         if (d_pair) cudaFree(d_pair);
         if (d_level_ptr) cudaFree(d_level_ptr);
     }
-    bool upload(const SlotLayout& lay, const TaskProgram& tp, std::string& err) {
-        (void)lay;
+    // xrow (optional, [n]): new name of X row k - the native layout names the rows of X by their
+    // position in the caller's x (the output permutation is folded into the program)
+    bool upload(const SlotLayout& lay, const TaskProgram& tp, std::string& err, const int* xrow = nullptr) {
+        const int nv = lay.n_val;
+        auto nm = [&](int idx) { return (xrow && idx >= nv) ? nv + xrow[idx - nv] : idx; };
         ntasks = static_cast<int>(tp.tasks.size());
         nlevels = tp.nlevels;
         n_mac = tp.n_mac;
@@ -51,11 +54,11 @@ struct LevelProg {
                 err = "dot product too long for the level program";
                 return false;
             }
-            rec[2 * t] = make_int4(k.out, k.div, k.pbeg + 1, k.plen | (static_cast<int>(k.kind) << 24));
-            rec[2 * t + 1] = k.plen ? make_int4(tp.pa[k.pbeg], tp.pb[k.pbeg], 0, 0) : make_int4(0, 0, 0, 0);
+            rec[2 * t] = make_int4(nm(k.out), k.div, k.pbeg + 1, k.plen | (static_cast<int>(k.kind) << 24));
+            rec[2 * t + 1] = k.plen ? make_int4(tp.pa[k.pbeg], nm(tp.pb[k.pbeg]), 0, 0) : make_int4(0, 0, 0, 0);
         }
         std::vector<int2> pr(std::max<size_t>(tp.pa.size(), 1));
-        for (size_t q = 0; q < tp.pa.size(); ++q) pr[q] = make_int2(tp.pa[q], tp.pb[q]);
+        for (size_t q = 0; q < tp.pa.size(); ++q) pr[q] = make_int2(tp.pa[q], nm(tp.pb[q]));
         for (int l = 0; l < nlevels; ++l)
             max_level_tasks = std::max(max_level_tasks, tp.level_ptr[l + 1] - tp.level_ptr[l]);
         auto up = [&](void** d, const void* src, size_t bytes) {
@@ -81,6 +84,7 @@ struct LevelCall {
     void* x = nullptr;
     const int *coo_dst = nullptr, *pattern_bad = nullptr, *rs_ptr = nullptr, *rs_slot = nullptr;
     const int *pnum = nullptr, *q = nullptr, *sysidx = nullptr;
+    const int *src_solve = nullptr, *src_tsolve = nullptr;  // native layout: row of b behind row j of x
     int32_t* status = nullptr;
     double* growth = nullptr;
     void* V = nullptr;   // [n_val][lpad] batch-interleaved, or [L][n_val] system-major
@@ -164,6 +168,15 @@ struct LvArgs {
     unsigned long long* growth2;    // [L] max |L|^2 as ordered bits
     int gsz;                        // cooperative kernels: CTAs that share one batch column
     unsigned* bar;                  // cooperative kernels: [columns] arrival counters (zeroed per launch)
+    // native layout of the solve (X = the caller's x[system][row][column], no relayout pass):
+    int native, n, lp_smem;         // lp_smem: the level table fits the dynamic shared memory of the launch
+    long long xss;                  // X[system * xss + row * xrs + column]
+    const void* B;                  // right-hand sides b[system * b_stride + row * r + column]
+    long long b_stride;
+    const int* src_of;              // row of b that output row j starts from (both permutations composed)
+    const double* Rs;               // row scale factors Rs[row * rlp + system * rss]
+    long long rlp, rss;
+    int scale_in, scale_out;        // solve: b / Rs on the way in; transpose solve: x / Rs on the way out
 };
 
 // ---- cooperative variants: several CTAs (SMs) per batch column --------------------------
@@ -235,13 +248,13 @@ template <typename T>
 __global__ void __launch_bounds__(1024) lv_solve_coop(const LvArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
-    const V_t* V = static_cast<const V_t*>(a.V);
-    V_t* X = static_cast<V_t*>(a.X);
     const int grp = blockIdx.x / a.gsz, rank = blockIdx.x % a.gsz;
     const long long q = grp;  // one right-hand-side column per group of CTAs
     if (q >= a.Q) return;
     const int m = static_cast<int>(q / a.r);
     const long long sm = a.sysidx ? a.sysidx[m] : m;
+    const V_t* vb = static_cast<const V_t*>(a.V) + sm * a.vss;
+    V_t* xb = static_cast<V_t*>(a.X) + (a.native ? (long long)m * a.xss + (q - (long long)m * a.r) : q * a.xcs);
     unsigned target = 0;
     unsigned* ctr = a.bar + grp;
     const int stride = a.gsz * blockDim.x, first = rank * blockDim.x + threadIdx.x;
@@ -253,140 +266,248 @@ __global__ void __launch_bounds__(1024) lv_solve_coop(const LvArgs a) {
             const int4 rec = __ldg(a.task + 2 * t), fp = __ldg(a.task + 2 * t + 1);
             const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
             const int2* pr = a.pair + rec.z;
-            V_t* o = X + (long long)(rec.x - a.n_val) * a.xrs + q * a.xcs;
+            V_t* o = xb + (long long)(rec.x - a.n_val) * a.xrs;
             const V_t o0 = __ldcg(o);
             V_t acc = S::zero();
             if (plen)
-                S::fma_acc(acc, __ldg(V + (long long)fp.x * a.lpad + sm * a.vss),
-                           __ldcg(X + (long long)(fp.y - a.n_val) * a.xrs + q * a.xcs));
+                S::fma_acc(acc, __ldg(vb + (long long)fp.x * a.lpad), __ldcg(xb + (long long)(fp.y - a.n_val) * a.xrs));
 #pragma unroll 4
             for (int p = 0; p < plen - 1; ++p) {
                 const int2 ab = __ldg(pr + p);
-                S::fma_acc(acc, __ldg(V + (long long)ab.x * a.lpad + sm * a.vss),
-                           __ldcg(X + (long long)(ab.y - a.n_val) * a.xrs + q * a.xcs));
+                S::fma_acc(acc, __ldg(vb + (long long)ab.x * a.lpad), __ldcg(xb + (long long)(ab.y - a.n_val) * a.xrs));
             }
             V_t v = S::sub(o0, acc);
-            if (kind >= TK_MUL) v = S::mul(v, __ldg(V + (long long)rec.y * a.lpad + sm * a.vss));
+            if (kind >= TK_MUL) v = S::mul(v, __ldg(vb + (long long)rec.y * a.lpad));
             *o = v;
         }
         group_barrier(ctr, a.gsz, target);
     }
 }
 
-// Refactorization: thread per (task, system) inside a level, CTA per slice of systems.
+// The level table in shared memory (one 30-cycle load per level instead of a global round trip
+// at the top of every level) when it fits the launch's dynamic shared memory.
+__device__ __forceinline__ const int* stage_level_table(const LvArgs& a, int* smem) {
+    if (!a.lp_smem) return a.level_ptr;
+    for (int i = threadIdx.x; i <= a.nlevels; i += blockDim.x) smem[i] = __ldg(a.level_ptr + i);
+    __syncthreads();
+    return smem;
+}
+
+// Refactorization.  A CTA owns a slice of `ncol` systems and walks ALL levels on it alone
+// (systems never interact: the barrier between levels is __syncthreads(), not a grid barrier,
+// and a CTA only ever reads values it wrote itself - same SM, coherent L1).  Inside the CTA a
+// thread is (column lane, task group): its system, and with it the base address of its values,
+// is fixed for the whole slice, the groups deal the tasks of a level between them - no division
+// and no 64-bit index arithmetic in the loops.
 template <typename T>
 __global__ void __launch_bounds__(1024) lv_factor(const LvArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
-    V_t* V = static_cast<V_t*>(a.V);
-    // Systems never interact, so a CTA owns a slice of the batch axis and walks ALL levels on
-    // it alone: the barrier between levels is __syncthreads(), not a grid-wide barrier, and a
-    // CTA only ever reads values it wrote itself (same SM, coherent L1).
+    extern __shared__ int lv_smem[];
+    const int* lp = stage_level_table(a, lv_smem);
+    const int lanes = a.slice, G = blockDim.x / lanes;
+    const int g = threadIdx.x / lanes, cl = threadIdx.x - g * lanes;
     for (long long s0 = (long long)blockIdx.x * a.slice; s0 < a.L; s0 += (long long)gridDim.x * a.slice) {
-        const int ncol = static_cast<int>(min((long long)a.slice, a.L - s0));
+        const bool on = g < G && s0 + cl < a.L;
+        const int m = on ? static_cast<int>(s0) + cl : 0;
+        V_t* vb = static_cast<V_t*>(a.V) + (a.sysidx ? (long long)a.sysidx[m] : (long long)m) * a.vss;
+        const long long lpad = a.lpad;
         // The task record of a thread's first item of the NEXT level is fetched before the
         // barrier, so a level costs one memory round trip (the operands), not two.
-        int te = __ldg(a.level_ptr), te_next = __ldg(a.level_ptr + 1);
+        int te = lp[0], te_next = lp[1];
         int4 pre_rec = make_int4(0, 0, 0, 0), pre_first = pre_rec;
-        if (static_cast<int>(threadIdx.x) < (te_next - te) * ncol) {
-            const int t0 = te + static_cast<int>(threadIdx.x) / ncol;
-            pre_rec = __ldg(a.task + 2 * t0);
-            pre_first = __ldg(a.task + 2 * t0 + 1);
+        if (on && te + g < te_next) {
+            pre_rec = __ldg(a.task + 2 * (te + g));
+            pre_first = __ldg(a.task + 2 * (te + g) + 1);
         }
         for (int l = 0; l < a.nlevels; ++l) {
             const int tb = te;
             te = te_next;
-            te_next = (l + 1 < a.nlevels) ? __ldg(a.level_ptr + l + 2) : te;
-            const int items = (te - tb) * ncol;
+            te_next = (l + 1 < a.nlevels) ? lp[l + 2] : te;
             const int4 cur_rec = pre_rec, cur_first = pre_first;
-            if (static_cast<int>(threadIdx.x) < (te_next - te) * ncol) {
-                const int t1 = te + static_cast<int>(threadIdx.x) / ncol;
-                pre_rec = __ldg(a.task + 2 * t1);
-                pre_first = __ldg(a.task + 2 * t1 + 1);
+            if (on && te + g < te_next) {
+                pre_rec = __ldg(a.task + 2 * (te + g));
+                pre_first = __ldg(a.task + 2 * (te + g) + 1);
             }
-            for (int it = threadIdx.x; it < items; it += blockDim.x) {
-                const int tq = it / ncol;
-                const int t = tb + tq, m = static_cast<int>(s0) + (it - tq * ncol);
-                const long long sm = a.sysidx ? a.sysidx[m] : m;
-                const bool pre = it == static_cast<int>(threadIdx.x);
-                const int4 rec = pre ? cur_rec : __ldg(a.task + 2 * t);
-                const int4 first = pre ? cur_first : __ldg(a.task + 2 * t + 1);
-                const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
-                const int2* pr = a.pair + rec.z;
-                V_t* o = V + (long long)rec.x * a.lpad + sm * a.vss;
-                const V_t o0 = *o;
-                V_t acc = S::zero();
-                if (plen) S::fma_acc(acc, V[(long long)first.x * a.lpad + sm * a.vss], V[(long long)first.y * a.lpad + sm * a.vss]);
+            if (on)
+                for (int t = tb + g; t < te; t += G) {
+                    const bool pre = t == tb + g;
+                    const int4 rec = pre ? cur_rec : __ldg(a.task + 2 * t);
+                    const int4 first = pre ? cur_first : __ldg(a.task + 2 * t + 1);
+                    const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
+                    const int2* pr = a.pair + rec.z;
+                    V_t* o = vb + rec.x * lpad;
+                    const V_t o0 = *o;
+                    V_t acc = S::zero();
+                    if (plen) S::fma_acc(acc, vb[first.x * lpad], vb[first.y * lpad]);
 #pragma unroll 4
-                for (int p = 0; p < plen - 1; ++p) {
-                    const int2 ab = __ldg(pr + p);
-                    const V_t x = V[(long long)ab.x * a.lpad + sm * a.vss];
-                    const V_t y = V[(long long)ab.y * a.lpad + sm * a.vss];
-                    S::fma_acc(acc, x, y);
+                    for (int p = 0; p < plen - 1; ++p) {
+                        const int2 ab = __ldg(pr + p);
+                        const V_t x = vb[ab.x * lpad];
+                        const V_t y = vb[ab.y * lpad];
+                        S::fma_acc(acc, x, y);
+                    }
+                    V_t v = S::sub(o0, acc);
+                    if (kind == TK_RECIP) {
+                        if (S::bad_pivot(v)) a.bad[m] = 1;
+                        v = S::recip(v);
+                    } else if (kind >= TK_MUL) {
+                        v = S::mul(v, vb[rec.y * lpad]);
+                        if (kind >= TK_MUL_TRACK)  // pivot-parity certificate, weighted by class (plan.hpp)
+                            atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v) * KB_TRACK_W2(kind - TK_MUL_TRACK)));
+                    }
+                    *o = v;
                 }
-                V_t v = S::sub(o0, acc);
-                if (kind == TK_RECIP) {
-                    if (S::bad_pivot(v)) a.bad[m] = 1;
-                    v = S::recip(v);
-                } else if (kind >= TK_MUL) {
-                    v = S::mul(v, V[(long long)rec.y * a.lpad + sm * a.vss]);
-                    if (kind >= TK_MUL_TRACK)
-                        atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v) * KB_TRACK_W2(kind - TK_MUL_TRACK)));
-                }
-                *o = v;
-            }
             __syncthreads();
         }
     }
 }
 
-// Triangular solves: thread per (task, right-hand-side column), CTA per slice of columns.
-template <typename T>
+// Triangular solves.  Right-hand-side columns (system m, column c: q = m*r + c) never interact
+// either: a CTA owns a slice of q and walks all levels on it, __syncthreads() between levels.
+// A thread is (column lane, task group) and owns C columns of the SAME system (lane, lane +
+// lanes, ...): the task record, the operand indices and the entry of L or U are loaded once and
+// used for C right-hand sides.  X is either the batch-interleaved scratch (X[row][q], many systems
+// with few right-hand sides each) or - native - the caller's x itself: the load b -> x with both
+// permutations composed (src_of) and the row scaling is the prologue of the slice, the scaling of
+// the transpose solve its epilogue, and the rows of X are named by their position in x, so nothing
+// is relaid out and no scratch is allocated.  PRE: prefetch of the next level's record as in
+// lv_factor (one column per CTA; with wide slices a thread runs many items per level and the extra
+// live registers cost more than they save: measured 3x slower on the multi-RHS solve of cfg 3).
+template <typename T, int C, bool PRE>
 __global__ void __launch_bounds__(1024) lv_solve(const LvArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
-    const V_t* V = static_cast<const V_t*>(a.V);
-    V_t* X = static_cast<V_t*>(a.X);
-    // Right-hand-side columns (system m, column c: q = m*r + c) never interact either: a CTA
-    // owns a slice of q and walks all levels on it, __syncthreads() between levels.
+    extern __shared__ int lv_smem[];
+    const int* lp = stage_level_table(a, lv_smem);
+    const int lanes = a.slice / C, G = blockDim.x / lanes;
+    const int g = threadIdx.x / lanes, cl = threadIdx.x - g * lanes;
     for (long long s0 = (long long)blockIdx.x * a.slice; s0 < a.Q; s0 += (long long)gridDim.x * a.slice) {
-        const int ncol = static_cast<int>(min((long long)a.slice, a.Q - s0));
-        // (no record prefetch here: measured 3x slower on the multi-RHS solve of cfg 3, where a
-        // thread runs many items per level and the extra live registers cost more than they save)
-        int te = __ldg(a.level_ptr);
-        for (int l = 0; l < a.nlevels; ++l) {
-            const int tb = te;
-            te = __ldg(a.level_ptr + l + 1);
-            const long long items = (long long)(te - tb) * ncol;
-            for (long long it = threadIdx.x; it < items; it += blockDim.x) {
-                const int tq = static_cast<int>(it / ncol);
-                const int t = tb + tq;
-                const long long q = s0 + (it - (long long)tq * ncol);
-                const int m = static_cast<int>(q / a.r);
-                const long long sm = a.sysidx ? a.sysidx[m] : m;
-                const int4 rec = __ldg(a.task + 2 * t), first = __ldg(a.task + 2 * t + 1);
-                const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
-                const int2* pr = a.pair + rec.z;
-                V_t* o = X + (long long)(rec.x - a.n_val) * a.xrs + q * a.xcs;
-                const V_t o0 = *o;
-                V_t acc = S::zero();
-                if (plen)
-                    S::fma_acc(acc, __ldg(V + (long long)first.x * a.lpad + sm * a.vss),
-                               X[(long long)(first.y - a.n_val) * a.xrs + q * a.xcs]);
-#pragma unroll 4
-                for (int p = 0; p < plen - 1; ++p) {
-                    const int2 ab = __ldg(pr + p);
-                    const V_t lu = __ldg(V + (long long)ab.x * a.lpad + sm * a.vss);
-                    const V_t xv = X[(long long)(ab.y - a.n_val) * a.xrs + q * a.xcs];
-                    S::fma_acc(acc, lu, xv);
-                }
-                V_t v = S::sub(o0, acc);
-                if (kind >= TK_MUL) v = S::mul(v, __ldg(V + (long long)rec.y * a.lpad + sm * a.vss));
-                *o = v;
+        bool ok[C];
+        V_t* xb[C];
+        const V_t* bb[C];
+        const long long q0 = s0 + cl;
+        const int m0 = static_cast<int>((q0 < a.Q ? q0 : 0) / a.r);
+        const long long sm = a.sysidx ? (long long)a.sysidx[m0] : (long long)m0;
+        const V_t* vb = static_cast<const V_t*>(a.V) + sm * a.vss;
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const long long q = q0 + (long long)j * lanes;
+            ok[j] = g < G && q < a.Q;
+            const long long qq = ok[j] ? q : 0;
+            const int c = static_cast<int>(qq - (long long)m0 * a.r);  // C > 1: the slice lies inside one system
+            xb[j] = static_cast<V_t*>(a.X) + (a.native ? (long long)m0 * a.xss + c : qq * a.xcs);
+            bb[j] = static_cast<const V_t*>(a.B) + (long long)m0 * a.b_stride + c;
+        }
+        const long long xrs = a.xrs, lpad = a.lpad;
+        const int nv = a.n_val;
+        if (a.native) {
+            for (int row = g; row < a.n; row += G) {
+                const int src = __ldg(a.src_of + row);
+                const double sc = a.scale_in ? a.Rs[(long long)src * a.rlp + sm * a.rss] : 1.0;
+#pragma unroll
+                for (int j = 0; j < C; ++j)
+                    if (ok[j]) {
+                        V_t v = bb[j][(long long)src * a.r];
+                        if (a.scale_in) v = S::rdiv(v, sc);
+                        xb[j][row * xrs] = v;
+                    }
             }
             __syncthreads();
         }
+        int te = lp[0], te_next = a.nlevels > 0 ? lp[1] : te;
+        int4 pre_rec = make_int4(0, 0, 0, 0), pre_first = pre_rec;
+        if (PRE && ok[0] && te + g < te_next) {
+            pre_rec = __ldg(a.task + 2 * (te + g));
+            pre_first = __ldg(a.task + 2 * (te + g) + 1);
+        }
+        for (int l = 0; l < a.nlevels; ++l) {
+            const int tb = te;
+            te = te_next;
+            te_next = (l + 1 < a.nlevels) ? lp[l + 2] : te;
+            const int4 cur_rec = pre_rec, cur_first = pre_first;
+            if (PRE && ok[0] && te + g < te_next) {
+                pre_rec = __ldg(a.task + 2 * (te + g));
+                pre_first = __ldg(a.task + 2 * (te + g) + 1);
+            }
+            if (ok[0])
+                for (int t = tb + g; t < te; t += G) {
+                    const bool pre = PRE && t == tb + g;
+                    const int4 rec = pre ? cur_rec : __ldg(a.task + 2 * t);
+                    const int4 first = pre ? cur_first : __ldg(a.task + 2 * t + 1);
+                    const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
+                    const int2* pr = a.pair + rec.z;
+                    const long long orow = (rec.x - nv) * xrs;
+                    V_t acc[C];
+#pragma unroll
+                    for (int j = 0; j < C; ++j) acc[j] = S::zero();
+                    if (plen) {
+                        const V_t lu = __ldg(vb + first.x * lpad);
+                        const long long xr = (first.y - nv) * xrs;
+#pragma unroll
+                        for (int j = 0; j < C; ++j)
+                            if (C == 1 || ok[j]) S::fma_acc(acc[j], lu, xb[j][xr]);
+                    }
+#pragma unroll 4
+                    for (int p = 0; p < plen - 1; ++p) {
+                        const int2 ab = __ldg(pr + p);
+                        const V_t lu = __ldg(vb + ab.x * lpad);
+                        const long long xr = (ab.y - nv) * xrs;
+#pragma unroll
+                        for (int j = 0; j < C; ++j)
+                            if (C == 1 || ok[j]) S::fma_acc(acc[j], lu, xb[j][xr]);
+                    }
+                    V_t dv = S::one();
+                    if (kind >= TK_MUL) dv = __ldg(vb + rec.y * lpad);
+#pragma unroll
+                    for (int j = 0; j < C; ++j)
+                        if (C == 1 || ok[j]) {
+                            V_t v = S::sub(xb[j][orow], acc[j]);
+                            if (kind >= TK_MUL) v = S::mul(v, dv);
+                            xb[j][orow] = v;
+                        }
+                }
+            __syncthreads();
+        }
+        if (a.native && a.scale_out) {
+            for (int row = g; row < a.n; row += G) {
+                const double sc = a.Rs[(long long)row * a.rlp + sm * a.rss];
+#pragma unroll
+                for (int j = 0; j < C; ++j)
+                    if (ok[j]) xb[j][row * xrs] = S::rdiv(xb[j][row * xrs], sc);
+            }
+        }
     }
+}
+
+// native layout for the cooperative solve (several CTAs per column: the prologue cannot live in
+// the kernel without one more group barrier): x[m][j][c] = b[m][src_of[j]][c] (/ Rs), and the
+// scaling of the transpose solve on the way out
+template <typename T>
+__global__ void lv_load_native(int L, int n, int r, const typename Sc<T>::V* __restrict__ b, long long b_stride,
+                               const int* __restrict__ src_of, int scale, const double* __restrict__ Rs,
+                               long long rlp, long long rss, const int* __restrict__ sysidx,
+                               typename Sc<T>::V* __restrict__ x) {
+    using S = Sc<T>;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)L * n * r) return;
+    const int c = static_cast<int>(tid % r);
+    const long long t2 = tid / r;
+    const int j = static_cast<int>(t2 % n), m = static_cast<int>(t2 / n);
+    const int src = src_of[j];
+    typename S::V v = b[(long long)m * b_stride + (long long)src * r + c];
+    if (scale) v = S::rdiv(v, Rs[(long long)src * rlp + (long long)(sysidx ? sysidx[m] : m) * rss]);
+    x[tid] = v;
+}
+template <typename T>
+__global__ void lv_scale_native(int L, int n, int r, const double* __restrict__ Rs, long long rlp, long long rss,
+                                const int* __restrict__ sysidx, typename Sc<T>::V* __restrict__ x) {
+    using S = Sc<T>;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)L * n * r) return;
+    const long long t2 = tid / r;
+    const int j = static_cast<int>(t2 % n), m = static_cast<int>(t2 / n);
+    x[tid] = S::rdiv(x[tid], Rs[(long long)j * rlp + (long long)(sysidx ? sysidx[m] : m) * rss]);
 }
 
 // X[k][m*r+c] = b[m][perm[k]][c] (/ Rs[perm[k]][m])
@@ -479,10 +600,31 @@ static int coop_group_size(K kernel, long long ncols, int slice, int num_sms, lo
 
 // Threads per CTA of the level kernels: enough for the widest level of the slice, at most 1024.
 static int level_threads(int max_level_tasks, int slice) {
-    if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_THREADS")) return std::max(32, std::min(1024, std::atoi(e)));
     (void)max_level_tasks;
-    (void)slice;
+    // at least one task group: a thread is (column lane, task group) and a slice has <= 64 lanes
+    if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_THREADS"))
+        return std::max((slice + 31) / 32 * 32, std::max(32, std::min(1024, std::atoi(e))));
     return 1024;
+}
+
+// The level table of a launch lives in shared memory up to this size (16 k levels); a larger
+// carve-out would take too much of the SM's L1, which caches the values and the rows of X.
+constexpr size_t kLevelTableSmem = 64 * 1024;
+
+// The solve runs on the caller's x (no scratch, no relayout) when a CTA owns one column, or when a
+// system has enough right-hand sides for a coalesced slice of them (x[system][row][column] is
+// contiguous along the columns); many systems with a few right-hand sides each go through the
+// batch-interleaved scratch, where consecutive threads = consecutive systems stay coalesced.
+static bool level_native(long long Q, int r, int num_sms) {
+    if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_NATIVE")) return std::atoi(e) != 0;
+    return pick_slice(Q, num_sms) == 1 || r >= 16;
+}
+
+template <typename K>
+static void launch_level(K kernel, int grid, int threads, size_t smem, cudaStream_t st, const LvArgs& a) {
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kLevelTableSmem));
+    kernel<<<grid, threads, smem, st>>>(a);
 }
 
 template <typename T>
@@ -549,7 +691,7 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
         const long long rt = (long long)c.n * c.L;
         lv_rowscale<T><<<static_cast<unsigned>((rt + 255) / 256), 256, 0, c.st>>>(
             c.L, c.n, c.rs_ptr, c.rs_slot, c.sysidx, V, Rs, v_slot, v_sys, r_row, r_sys);
-        LvArgs a;
+        LvArgs a = {};
         a.task = pf->d_task; a.pair = pf->d_pair; a.level_ptr = pf->d_level_ptr;
         a.nlevels = pf->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = 1; a.lpad = v_slot; a.vss = v_sys; a.xrs = 0; a.xcs = 0; a.Q = c.L;
         a.V = V; a.X = nullptr; a.sysidx = c.sysidx; a.bad = bad; a.growth2 = growth2;
@@ -566,7 +708,9 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
                 return KLU_OUT_OF_MEMORY;
             }
         } else {
-            lv_factor<T><<<grid, level_threads(pf->max_level_tasks, a.slice), 0, c.st>>>(a);
+            const size_t lp_bytes = sizeof(int) * (static_cast<size_t>(pf->nlevels) + 1);
+            a.lp_smem = lp_bytes <= kLevelTableSmem ? 1 : 0;
+            launch_level(lv_factor<T>, grid, level_threads(pf->max_level_tasks, a.slice), a.lp_smem ? lp_bytes : 0, c.st, a);
         }
         lv_finish_status<<<(c.L + 255) / 256, 256, 0, c.st>>>(c.L, bad, growth2, c.pattern_bad,
                                                             c.status, c.growth, c.certify);
@@ -574,40 +718,69 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
     if (ps) {
         const bool tr = (c.mode == PM_FACTOR_TSOLVE || c.mode == PM_TSOLVE);
         const long long Q = (long long)c.L * c.r;
-        if (!chk(cudaMallocAsync(&tmpX, sizeof(V_t) * (size_t)c.n * Q, c.st), "alloc X")) {
-            cleanup();
-            return KLU_OUT_OF_MEMORY;
-        }
-        V_t* X = static_cast<V_t*>(tmpX);
         const long long tot = Q * c.n;
-        // X: columns interleaved (X[row][column]) for wide slices, column-major for one column per CTA
         const int xslice = pick_slice(Q, c.num_sms);
-        const long long x_row = xslice == 1 ? 1 : Q, x_col = xslice == 1 ? c.n : 1;
-        lv_load_x<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
-            c.L, c.n, c.r, static_cast<const V_t*>(c.b), c.b_stride, tr ? c.q : c.pnum, tr ? 0 : 1,
-            Rs, r_row, r_sys, c.sysidx, X, x_row, x_col);
-        LvArgs a;
+        const bool native = level_native(Q, c.r, c.num_sms);
+        V_t* X = static_cast<V_t*>(c.x);
+        // X: the caller's x (native), else a scratch with the columns interleaved (X[row][column])
+        long long x_row = c.r, x_col = 0;
+        if (!native) {
+            if (!chk(cudaMallocAsync(&tmpX, sizeof(V_t) * (size_t)c.n * Q, c.st), "alloc X")) {
+                cleanup();
+                return KLU_OUT_OF_MEMORY;
+            }
+            X = static_cast<V_t*>(tmpX);
+            x_row = Q;
+            x_col = 1;
+            lv_load_x<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
+                c.L, c.n, c.r, static_cast<const V_t*>(c.b), c.b_stride, tr ? c.q : c.pnum, tr ? 0 : 1,
+                Rs, r_row, r_sys, c.sysidx, X, x_row, x_col);
+        }
+        LvArgs a = {};
         a.task = ps->d_task; a.pair = ps->d_pair; a.level_ptr = ps->d_level_ptr;
         a.nlevels = ps->nlevels; a.n_val = c.n_val; a.L = c.L; a.r = c.r; a.lpad = v_slot; a.vss = v_sys; a.xrs = x_row; a.xcs = x_col; a.Q = Q;
         a.V = V; a.X = X; a.sysidx = c.sysidx; a.bad = bad; a.growth2 = growth2;
         a.slice = xslice;
+        a.native = native ? 1 : 0; a.n = c.n; a.xss = (long long)c.n * c.r;
+        a.B = c.b; a.b_stride = c.b_stride; a.src_of = tr ? c.src_tsolve : c.src_solve;
+        a.Rs = Rs; a.rlp = r_row; a.rss = r_sys; a.scale_in = tr ? 0 : 1; a.scale_out = tr ? 1 : 0;
+        const size_t lp_bytes = sizeof(int) * (static_cast<size_t>(ps->nlevels) + 1);
+        a.lp_smem = lp_bytes <= kLevelTableSmem ? 1 : 0;
         const int grid = static_cast<int>(std::min<long long>((Q + a.slice - 1) / a.slice, 2LL * c.num_sms));
         a.gsz = coop_bar ? coop_group_size(lv_solve_coop<T>, Q, a.slice, c.num_sms, ps->ntasks, ps->nlevels) : 0;
         if (a.gsz >= 2) {
             a.bar = coop_bar;
             void* kargs[] = {&a};
+            if (native)
+                lv_load_native<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
+                    c.L, c.n, c.r, static_cast<const V_t*>(c.b), c.b_stride, a.src_of, a.scale_in, Rs, r_row, r_sys,
+                    c.sysidx, X);
             if (!chk(cudaMemsetAsync(coop_bar, 0, sizeof(unsigned) * Q, c.st), "memset barrier") ||
                 !chk(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lv_solve_coop<T>), dim3(static_cast<unsigned>(Q * a.gsz)),
                                                  dim3(1024), kargs, 0, c.st), "cooperative solve")) {
                 cleanup();
                 return KLU_OUT_OF_MEMORY;
             }
+            if (native && a.scale_out)
+                lv_scale_native<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
+                    c.L, c.n, c.r, Rs, r_row, r_sys, c.sysidx, X);
         } else {
-            lv_solve<T><<<grid, level_threads(ps->max_level_tasks, a.slice), 0, c.st>>>(a);
+            const int threads = level_threads(ps->max_level_tasks, a.slice);
+            const size_t sm_bytes = a.lp_smem ? lp_bytes : 0;
+            // two right-hand sides per thread when the slice is two warps of columns of one system
+            int C = (native && a.slice % 64 == 0 && c.r % a.slice == 0) ? 2 : 1;
+            if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_C")) C = (std::atoi(e) == 2 && C == 2) ? 2 : 1;
+            if (a.slice == 1)
+                launch_level(lv_solve<T, 1, true>, grid, threads, sm_bytes, c.st, a);
+            else if (C == 2)
+                launch_level(lv_solve<T, 2, false>, grid, threads, sm_bytes, c.st, a);
+            else
+                launch_level(lv_solve<T, 1, false>, grid, threads, sm_bytes, c.st, a);
         }
-        lv_store_x<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
-            c.L, c.n, c.r, static_cast<V_t*>(c.x), tr ? c.pnum : c.q, tr ? 1 : 0, Rs, r_row, r_sys, c.sysidx, X,
-            x_row, x_col);
+        if (!native)
+            lv_store_x<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(
+                c.L, c.n, c.r, static_cast<V_t*>(c.x), tr ? c.pnum : c.q, tr ? 1 : 0, Rs, r_row, r_sys, c.sysidx, X,
+                x_row, x_col);
     }
     if (!chk(cudaGetLastError(), "level kernels")) {
         cleanup();

@@ -101,6 +101,7 @@ struct Seeded {
     SlotLayout lay;
     int regime = 0;  // 0 = shared-memory warp-per-system, 1 = level-scheduled global
     DevBuf d_colptr, d_srow, d_sslot, d_rs_ptr, d_rs_slot, d_pnum, d_q;
+    DevBuf d_src_solve, d_src_tsolve;  // level solves on the caller's x: source row of b per row of x
     std::map<std::pair<int, int>, std::unique_ptr<SmallProg>> small;  // key (mode, rc + 1000 * wide)
     std::map<std::pair<int, int>, std::unique_ptr<LevelProg>> level;
     std::map<std::pair<int, int>, std::unique_ptr<RRKernel>> rowreg;  // key (transpose, n_rhs)
@@ -214,6 +215,17 @@ static int upload_seeded(Symbolic* S, int cx) {
     CUDA_OK(sd.d_rs_slot.upload(sd.lay.rs_slot));
     CUDA_OK(sd.d_pnum.upload(sd.piv.Pnum));
     CUDA_OK(sd.d_q.upload(S->ord.Q));
+    {
+        // solve: x[Q[k]] <- b[Pnum[k]]; transpose solve: x[Pnum[k]] <- b[Q[k]] (klu_solve / klu_tsolve)
+        const int n = sd.lay.n;
+        std::vector<int> ss(n), st(n);
+        for (int k = 0; k < n; ++k) {
+            ss[S->ord.Q[k]] = sd.piv.Pnum[k];
+            st[sd.piv.Pnum[k]] = S->ord.Q[k];
+        }
+        CUDA_OK(sd.d_src_solve.upload(ss));
+        CUDA_OK(sd.d_src_tsolve.upload(st));
+    }
     return 0;
 }
 
@@ -315,7 +327,7 @@ static int get_small_prog(Symbolic* S, int cx, int mode, int rc, bool wide, bool
     return 0;
 }
 
-static int get_level_prog(Symbolic* S, int cx, int mode, long long batch_cols, LevelProg** out) {
+static int get_level_prog(Symbolic* S, int cx, int mode, long long batch_cols, LevelProg** out, bool native = false) {
     Seeded& sd = S->seeded[cx];
     // Task granularity (plan.cpp: Leveler): with few batch columns the time per level is one
     // memory round trip, so every multiply-add is applied as soon as its operands are final
@@ -334,14 +346,16 @@ static int get_level_prog(Symbolic* S, int cx, int mode, long long batch_cols, L
         split = batch_cols >= 4096 ? 3 : 2;
     }
     if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_SPLIT")) split = std::atoi(e);
-    auto key = std::make_pair(mode, split);
+    auto key = std::make_pair(mode, split + (native ? 1000 : 0));
     auto it = sd.level.find(key);
     if (it == sd.level.end()) {
         TaskProgram tp;
         build_program(S->ord, sd.piv, sd.lay, mode, 1, tp, split);
         auto lp = std::make_unique<LevelProg>();
         std::string err;
-        if (!lp->upload(sd.lay, tp, err)) return fail(KLU_OUT_OF_MEMORY, err);
+        // native: the rows of X carry the names of their final positions in x
+        const int* xrow = !native ? nullptr : (mode == PM_TSOLVE ? sd.piv.Pnum.data() : S->ord.Q.data());
+        if (!lp->upload(sd.lay, tp, err, xrow)) return fail(KLU_OUT_OF_MEMORY, err);
         if (mode == PM_FACTOR) sd.info_levels = tp.nlevels;
         it = sd.level.emplace(key, std::move(lp)).first;
     }
@@ -726,6 +740,8 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
     lc.rs_slot = sd.d_rs_slot.as<int>();
     lc.pnum = sd.d_pnum.as<int>();
     lc.q = sd.d_q.as<int>();
+    lc.src_solve = sd.d_src_solve.as<int>();
+    lc.src_tsolve = sd.d_src_tsolve.as<int>();
     lc.sysidx = op.sysidx_dev;
     lc.status = op.status;
     lc.growth = op.growth;
@@ -749,7 +765,8 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
     }
     if (op.mode != PM_FACTOR) {
         const bool tr = (op.mode == PM_FACTOR_TSOLVE || op.mode == PM_TSOLVE);
-        int e = get_level_prog(S, cx, tr ? PM_TSOLVE : PM_SOLVE, static_cast<long long>(op.L) * op.r, &ps);
+        const long long Q = static_cast<long long>(op.L) * op.r;
+        int e = get_level_prog(S, cx, tr ? PM_TSOLVE : PM_SOLVE, Q, &ps, level_native(Q, op.r, lc.num_sms));
         if (e) return e;
     }
     std::string err;
