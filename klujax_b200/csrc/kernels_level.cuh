@@ -42,8 +42,14 @@ struct LevelProg {
     // xrow (optional, [n]): new name of X row k - the native layout names the rows of X by their
     // position in the caller's x (the output permutation is folded into the program)
     bool upload(const SlotLayout& lay, const TaskProgram& tp, std::string& err, const int* xrow = nullptr) {
+        // Solve programs address X by row: the records hold the row itself (index - n_val, renamed
+        // by xrow), the kernels never subtract n_val.
         const int nv = lay.n_val;
-        auto nm = [&](int idx) { return (xrow && idx >= nv) ? nv + xrow[idx - nv] : idx; };
+        const bool solve_prog = tp.mode == PM_SOLVE || tp.mode == PM_TSOLVE;
+        auto nm = [&](int idx) {
+            if (!solve_prog) return idx;
+            return xrow ? xrow[idx - nv] : idx - nv;
+        };
         ntasks = static_cast<int>(tp.tasks.size());
         nlevels = tp.nlevels;
         n_mac = tp.n_mac;
@@ -266,15 +272,15 @@ __global__ void __launch_bounds__(1024) lv_solve_coop(const LvArgs a) {
             const int4 rec = __ldg(a.task + 2 * t), fp = __ldg(a.task + 2 * t + 1);
             const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
             const int2* pr = a.pair + rec.z;
-            V_t* o = xb + (long long)(rec.x - a.n_val) * a.xrs;
+            V_t* o = xb + (long long)rec.x * a.xrs;
             const V_t o0 = __ldcg(o);
             V_t acc = S::zero();
             if (plen)
-                S::fma_acc(acc, __ldg(vb + (long long)fp.x * a.lpad), __ldcg(xb + (long long)(fp.y - a.n_val) * a.xrs));
+                S::fma_acc(acc, __ldg(vb + (long long)fp.x * a.lpad), __ldcg(xb + (long long)fp.y * a.xrs));
 #pragma unroll 4
             for (int p = 0; p < plen - 1; ++p) {
                 const int2 ab = __ldg(pr + p);
-                S::fma_acc(acc, __ldg(vb + (long long)ab.x * a.lpad), __ldcg(xb + (long long)(ab.y - a.n_val) * a.xrs));
+                S::fma_acc(acc, __ldg(vb + (long long)ab.x * a.lpad), __ldcg(xb + (long long)ab.y * a.xrs));
             }
             V_t v = S::sub(o0, acc);
             if (kind >= TK_MUL) v = S::mul(v, __ldg(vb + (long long)rec.y * a.lpad));
@@ -311,7 +317,10 @@ __global__ void __launch_bounds__(1024) lv_factor(const LvArgs a) {
         const bool on = g < G && s0 + cl < a.L;
         const int m = on ? static_cast<int>(s0) + cl : 0;
         V_t* vb = static_cast<V_t*>(a.V) + (a.sysidx ? (long long)a.sysidx[m] : (long long)m) * a.vss;
-        const long long lpad = a.lpad;
+        const unsigned lpb = static_cast<unsigned>(a.lpad * sizeof(V_t));  // see lv_solve
+        auto vp = [&](int slot) {
+            return reinterpret_cast<V_t*>(reinterpret_cast<char*>(vb) + (unsigned long long)static_cast<unsigned>(slot) * lpb);
+        };
         // The task record of a thread's first item of the NEXT level is fetched before the
         // barrier, so a level costs one memory round trip (the operands), not two.
         int te = lp[0], te_next = lp[1];
@@ -336,15 +345,15 @@ __global__ void __launch_bounds__(1024) lv_factor(const LvArgs a) {
                     const int4 first = pre ? cur_first : __ldg(a.task + 2 * t + 1);
                     const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
                     const int2* pr = a.pair + rec.z;
-                    V_t* o = vb + rec.x * lpad;
+                    V_t* o = vp(rec.x);
                     const V_t o0 = *o;
                     V_t acc = S::zero();
-                    if (plen) S::fma_acc(acc, vb[first.x * lpad], vb[first.y * lpad]);
+                    if (plen) S::fma_acc(acc, *vp(first.x), *vp(first.y));
 #pragma unroll 4
                     for (int p = 0; p < plen - 1; ++p) {
                         const int2 ab = __ldg(pr + p);
-                        const V_t x = vb[ab.x * lpad];
-                        const V_t y = vb[ab.y * lpad];
+                        const V_t x = *vp(ab.x);
+                        const V_t y = *vp(ab.y);
                         S::fma_acc(acc, x, y);
                     }
                     V_t v = S::sub(o0, acc);
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(1024) lv_factor(const LvArgs a) {
                         if (S::bad_pivot(v)) a.bad[m] = 1;
                         v = S::recip(v);
                     } else if (kind >= TK_MUL) {
-                        v = S::mul(v, vb[rec.y * lpad]);
+                        v = S::mul(v, *vp(rec.y));
                         if (kind >= TK_MUL_TRACK)  // pivot-parity certificate, weighted by class (plan.hpp)
                             atomicMax(a.growth2 + m, (unsigned long long)__double_as_longlong(S::mag2(v) * KB_TRACK_W2(kind - TK_MUL_TRACK)));
                     }
@@ -363,19 +372,48 @@ __global__ void __launch_bounds__(1024) lv_factor(const LvArgs a) {
     }
 }
 
+// C adjacent values as 16-byte vector accesses (C * sizeof(V) is a multiple of 16 when C > 1)
+template <typename V_t, int C>
+__device__ __forceinline__ void ld_cols(const V_t* p, V_t (&v)[C]) {
+    if constexpr (C * sizeof(V_t) % 16 == 0) {
+        constexpr int NV = C * sizeof(V_t) / 16;
+        double2 t[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) t[i] = reinterpret_cast<const double2*>(p)[i];
+        memcpy(v, t, sizeof(t));
+    } else {
+#pragma unroll
+        for (int j = 0; j < C; ++j) v[j] = p[j];
+    }
+}
+template <typename V_t, int C>
+__device__ __forceinline__ void st_cols(V_t* p, const V_t (&v)[C]) {
+    if constexpr (C * sizeof(V_t) % 16 == 0) {
+        constexpr int NV = C * sizeof(V_t) / 16;
+        double2 t[NV];
+        memcpy(t, v, sizeof(t));
+#pragma unroll
+        for (int i = 0; i < NV; ++i) reinterpret_cast<double2*>(p)[i] = t[i];
+    } else {
+#pragma unroll
+        for (int j = 0; j < C; ++j) p[j] = v[j];
+    }
+}
+
 // Triangular solves.  Right-hand-side columns (system m, column c: q = m*r + c) never interact
 // either: a CTA owns a slice of q and walks all levels on it, __syncthreads() between levels.
-// A thread is (column lane, task group) and owns C columns of the SAME system (lane, lane +
-// lanes, ...): the task record, the operand indices and the entry of L or U are loaded once and
-// used for C right-hand sides.  X is either the batch-interleaved scratch (X[row][q], many systems
-// with few right-hand sides each) or - native - the caller's x itself: the load b -> x with both
-// permutations composed (src_of) and the row scaling is the prologue of the slice, the scaling of
-// the transpose solve its epilogue, and the rows of X are named by their position in x, so nothing
-// is relaid out and no scratch is allocated.  PRE: prefetch of the next level's record as in
-// lv_factor (one column per CTA; with wide slices a thread runs many items per level and the extra
-// live registers cost more than they save: measured 3x slower on the multi-RHS solve of cfg 3).
+// A thread is (column lane, task group) and owns C ADJACENT columns (C divides r, so they belong
+// to one system and are one aligned vector access): the task record, the operand indices and the
+// entry of L or U are loaded once and used for C right-hand sides.  X is either the
+// batch-interleaved scratch (X[row][q], many systems with few right-hand sides each; C = 1) or -
+// native - the caller's x itself: the load b -> x with both permutations composed (src_of) and the
+// row scaling is the prologue of the slice, the scaling of the transpose solve its epilogue, and
+// the rows of X are named by their position in x, so nothing is relaid out and no scratch is
+// allocated.  PRE: prefetch of the next level's record as in lv_factor (one column per CTA; with
+// wide slices a thread runs many items per level and the extra live registers cost more than
+// they save: measured 3x slower on the multi-RHS solve of cfg 3).
 template <typename T, int C, bool PRE>
-__global__ void __launch_bounds__(1024) lv_solve(const LvArgs a) {
+__global__ void __launch_bounds__(C >= 8 ? 768 : 1024) lv_solve(const LvArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
     extern __shared__ int lv_smem[];
@@ -383,41 +421,42 @@ __global__ void __launch_bounds__(1024) lv_solve(const LvArgs a) {
     const int lanes = a.slice / C, G = blockDim.x / lanes;
     const int g = threadIdx.x / lanes, cl = threadIdx.x - g * lanes;
     for (long long s0 = (long long)blockIdx.x * a.slice; s0 < a.Q; s0 += (long long)gridDim.x * a.slice) {
-        bool ok[C];
-        V_t* xb[C];
-        const V_t* bb[C];
-        const long long q0 = s0 + cl;
-        const int m0 = static_cast<int>((q0 < a.Q ? q0 : 0) / a.r);
+        const long long q0 = s0 + (long long)cl * C;
+        const bool ok = g < G && q0 < a.Q;  // Q is a multiple of C: all C columns or none
+        const int m0 = static_cast<int>((ok ? q0 : 0) / a.r);
+        const int c0 = ok ? static_cast<int>(q0 - (long long)m0 * a.r) : 0;
         const long long sm = a.sysidx ? (long long)a.sysidx[m0] : (long long)m0;
         const V_t* vb = static_cast<const V_t*>(a.V) + sm * a.vss;
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-            const long long q = q0 + (long long)j * lanes;
-            ok[j] = g < G && q < a.Q;
-            const long long qq = ok[j] ? q : 0;
-            const int c = static_cast<int>(qq - (long long)m0 * a.r);  // C > 1: the slice lies inside one system
-            xb[j] = static_cast<V_t*>(a.X) + (a.native ? (long long)m0 * a.xss + c : qq * a.xcs);
-            bb[j] = static_cast<const V_t*>(a.B) + (long long)m0 * a.b_stride + c;
-        }
-        const long long xrs = a.xrs, lpad = a.lpad;
-        const int nv = a.n_val;
+        V_t* xb = static_cast<V_t*>(a.X) + (a.native ? (long long)m0 * a.xss + c0 : (ok ? q0 : 0) * a.xcs);
+        const V_t* bb = static_cast<const V_t*>(a.B) + (long long)m0 * a.b_stride + c0;
+        // addresses = 64-bit base + 32-bit index x 32-bit byte stride: one IMAD.WIDE.U32 each (the
+        // host checks that the strides fit; a 64-bit index product costs ~10 instructions)
+        const unsigned xrb = static_cast<unsigned>(a.xrs * sizeof(V_t)), lpb = static_cast<unsigned>(a.lpad * sizeof(V_t));
+        auto xp = [&](int row) {
+            return reinterpret_cast<V_t*>(reinterpret_cast<char*>(xb) + (unsigned long long)static_cast<unsigned>(row) * xrb);
+        };
+        auto vp = [&](int slot) {
+            return reinterpret_cast<const V_t*>(reinterpret_cast<const char*>(vb) +
+                                                (unsigned long long)static_cast<unsigned>(slot) * lpb);
+        };
         if (a.native) {
-            for (int row = g; row < a.n; row += G) {
-                const int src = __ldg(a.src_of + row);
-                const double sc = a.scale_in ? a.Rs[(long long)src * a.rlp + sm * a.rss] : 1.0;
+            if (ok)
+                for (int row = g; row < a.n; row += G) {
+                    const int src = __ldg(a.src_of + row);
+                    V_t v[C];
+                    ld_cols<V_t, C>(bb + (long long)src * a.r, v);
+                    if (a.scale_in) {
+                        const double sc = a.Rs[(long long)src * a.rlp + sm * a.rss];
 #pragma unroll
-                for (int j = 0; j < C; ++j)
-                    if (ok[j]) {
-                        V_t v = bb[j][(long long)src * a.r];
-                        if (a.scale_in) v = S::rdiv(v, sc);
-                        xb[j][row * xrs] = v;
+                        for (int j = 0; j < C; ++j) v[j] = S::rdiv(v[j], sc);
                     }
-            }
+                    st_cols<V_t, C>(xp(row), v);
+                }
             __syncthreads();
         }
         int te = lp[0], te_next = a.nlevels > 0 ? lp[1] : te;
         int4 pre_rec = make_int4(0, 0, 0, 0), pre_first = pre_rec;
-        if (PRE && ok[0] && te + g < te_next) {
+        if (PRE && ok && te + g < te_next) {
             pre_rec = __ldg(a.task + 2 * (te + g));
             pre_first = __ldg(a.task + 2 * (te + g) + 1);
         }
@@ -426,55 +465,55 @@ __global__ void __launch_bounds__(1024) lv_solve(const LvArgs a) {
             te = te_next;
             te_next = (l + 1 < a.nlevels) ? lp[l + 2] : te;
             const int4 cur_rec = pre_rec, cur_first = pre_first;
-            if (PRE && ok[0] && te + g < te_next) {
+            if (PRE && ok && te + g < te_next) {
                 pre_rec = __ldg(a.task + 2 * (te + g));
                 pre_first = __ldg(a.task + 2 * (te + g) + 1);
             }
-            if (ok[0])
+            if (ok)
                 for (int t = tb + g; t < te; t += G) {
                     const bool pre = PRE && t == tb + g;
                     const int4 rec = pre ? cur_rec : __ldg(a.task + 2 * t);
                     const int4 first = pre ? cur_first : __ldg(a.task + 2 * t + 1);
                     const int plen = rec.w & 0xFFFFFF, kind = rec.w >> 24;
                     const int2* pr = a.pair + rec.z;
-                    const long long orow = (rec.x - nv) * xrs;
-                    V_t acc[C];
+                    V_t* o = xp(rec.x);
+                    V_t acc[C], xv[C];
 #pragma unroll
                     for (int j = 0; j < C; ++j) acc[j] = S::zero();
                     if (plen) {
-                        const V_t lu = __ldg(vb + first.x * lpad);
-                        const long long xr = (first.y - nv) * xrs;
+                        const V_t lu = __ldg(vp(first.x));
+                        ld_cols<V_t, C>(xp(first.y), xv);
 #pragma unroll
-                        for (int j = 0; j < C; ++j)
-                            if (C == 1 || ok[j]) S::fma_acc(acc[j], lu, xb[j][xr]);
+                        for (int j = 0; j < C; ++j) S::fma_acc(acc[j], lu, xv[j]);
                     }
 #pragma unroll 4
                     for (int p = 0; p < plen - 1; ++p) {
                         const int2 ab = __ldg(pr + p);
-                        const V_t lu = __ldg(vb + ab.x * lpad);
-                        const long long xr = (ab.y - nv) * xrs;
+                        const V_t lu = __ldg(vp(ab.x));
+                        ld_cols<V_t, C>(xp(ab.y), xv);
 #pragma unroll
-                        for (int j = 0; j < C; ++j)
-                            if (C == 1 || ok[j]) S::fma_acc(acc[j], lu, xb[j][xr]);
+                        for (int j = 0; j < C; ++j) S::fma_acc(acc[j], lu, xv[j]);
                     }
                     V_t dv = S::one();
-                    if (kind >= TK_MUL) dv = __ldg(vb + rec.y * lpad);
+                    if (kind >= TK_MUL) dv = __ldg(vp(rec.y));
+                    ld_cols<V_t, C>(o, xv);
 #pragma unroll
-                    for (int j = 0; j < C; ++j)
-                        if (C == 1 || ok[j]) {
-                            V_t v = S::sub(xb[j][orow], acc[j]);
-                            if (kind >= TK_MUL) v = S::mul(v, dv);
-                            xb[j][orow] = v;
-                        }
+                    for (int j = 0; j < C; ++j) {
+                        xv[j] = S::sub(xv[j], acc[j]);
+                        if (kind >= TK_MUL) xv[j] = S::mul(xv[j], dv);
+                    }
+                    st_cols<V_t, C>(o, xv);
                 }
             __syncthreads();
         }
-        if (a.native && a.scale_out) {
+        if (a.native && a.scale_out && ok) {
             for (int row = g; row < a.n; row += G) {
                 const double sc = a.Rs[(long long)row * a.rlp + sm * a.rss];
+                V_t v[C];
+                ld_cols<V_t, C>(xp(row), v);
 #pragma unroll
-                for (int j = 0; j < C; ++j)
-                    if (ok[j]) xb[j][row * xrs] = S::rdiv(xb[j][row * xrs], sc);
+                for (int j = 0; j < C; ++j) v[j] = S::rdiv(v[j], sc);
+                st_cols<V_t, C>(xp(row), v);
             }
         }
     }
@@ -620,6 +659,22 @@ static bool level_native(long long Q, int r, int num_sms) {
     return pick_slice(Q, num_sms) == 1 || r >= 16;
 }
 
+// Columns per CTA of the native multi-right-hand-side solve.  A CTA of 1024 threads fills an SM
+// (56-64 registers per thread), so the slices are sized for whole, balanced waves of num_sms
+// CTAs: 16 384 columns on 148 SMs are 148 slices of 112 (one wave), not 256 slices of 64 (a full
+// wave and a 73 % one).  At most 128 columns: wider slices lose the rows of X from L1.
+static int native_slice(long long Q, int num_sms, int C) {
+    int waves = 1;
+    long long per = (Q + num_sms - 1) / num_sms;
+    int cap = 128;
+    if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_MAXSLICE")) cap = std::max(C, std::atoi(e));
+    while (per > cap) {
+        ++waves;
+        per = (Q + (long long)num_sms * waves - 1) / ((long long)num_sms * waves);
+    }
+    return static_cast<int>(std::max<long long>(C, (per + C - 1) / C * C));
+}
+
 template <typename K>
 static void launch_level(K kernel, int grid, int threads, size_t smem, cudaStream_t st, const LvArgs& a) {
     if (smem > 48 * 1024)
@@ -679,6 +734,11 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
     unsigned* coop_bar = ncnt <= 1024 ? reinterpret_cast<unsigned*>(bad + ((c.L + 15) / 16) * 16) : nullptr;
 
     const long long v_slot = sysmajor ? 1 : lpad, v_sys = sysmajor ? c.n_val : 1;
+    if (v_slot * 16 >= (1LL << 32) || (long long)c.L * std::max(c.r, 1) * 16 >= (1LL << 32)) {
+        err = "batch too large for the 32-bit strides of the level kernels (split the batch)";
+        cleanup();
+        return KLU_TOO_LARGE;
+    }
     const long long r_row = sysmajor ? 1 : lpad, r_sys = sysmajor ? c.n : 1;
     const bool factor = (pf != nullptr);
     if (factor) {
@@ -767,15 +827,28 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
         } else {
             const int threads = level_threads(ps->max_level_tasks, a.slice);
             const size_t sm_bytes = a.lp_smem ? lp_bytes : 0;
-            // two right-hand sides per thread when the slice is two warps of columns of one system
-            int C = (native && a.slice % 64 == 0 && c.r % a.slice == 0) ? 2 : 1;
-            if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_C")) C = (std::atoi(e) == 2 && C == 2) ? 2 : 1;
+            // C adjacent right-hand sides per thread (native layout; C divides r and the slice)
+            int C = 1;
+            if (native && a.slice > 1) {
+                C = (c.r % 4 == 0 && !c.is_complex) ? 4 : (c.r % 2 == 0 ? 2 : 1);
+                if (const char* e = std::getenv("KLUJAX_CUDA_LEVEL_C")) {
+                    const int want = std::atoi(e);
+                    if ((want == 1 || want == 2 || want == 4 || (want == 8 && !c.is_complex)) && c.r % want == 0) C = want;
+                }
+                if (!std::getenv("KLUJAX_CUDA_LEVEL_SLICE")) a.slice = native_slice(Q, c.num_sms, C);
+                a.slice = std::max(C, a.slice / C * C);
+            }
+            const int grid2 = static_cast<int>(std::min<long long>((Q + a.slice - 1) / a.slice, 2LL * c.num_sms));
             if (a.slice == 1)
-                launch_level(lv_solve<T, 1, true>, grid, threads, sm_bytes, c.st, a);
+                launch_level(lv_solve<T, 1, true>, grid2, threads, sm_bytes, c.st, a);
+            else if (C == 8)
+                launch_level(lv_solve<double, 8, false>, grid2, std::min(threads, 768), sm_bytes, c.st, a);
+            else if (C == 4)
+                launch_level(lv_solve<T, 4, false>, grid2, threads, sm_bytes, c.st, a);
             else if (C == 2)
-                launch_level(lv_solve<T, 2, false>, grid, threads, sm_bytes, c.st, a);
+                launch_level(lv_solve<T, 2, false>, grid2, threads, sm_bytes, c.st, a);
             else
-                launch_level(lv_solve<T, 1, false>, grid, threads, sm_bytes, c.st, a);
+                launch_level(lv_solve<T, 1, false>, grid2, threads, sm_bytes, c.st, a);
         }
         if (!native)
             lv_store_x<T><<<static_cast<unsigned>((tot + 255) / 256), 256, 0, c.st>>>(

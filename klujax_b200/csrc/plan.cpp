@@ -414,6 +414,8 @@ void build_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& 
     // solves only, 2 = everywhere, 3 = everywhere in groups of at least 8 multiply-adds
     Leveler lv(lay.n_val + nx, prog, split >= 2);
     if (split == 3) lv.min_group = 8;
+    if (split == 5) lv.min_group = 16;
+    if (split == 6) lv.min_group = 32;
     if (split == 4) lv.single = true;  // single multiply-add tasks
     if (split >= 100) {                // 100 + 10*min + max: bounded groups (multi-warp shared-memory kernel)
         lv.min_group = (split - 100) / 10;
