@@ -104,6 +104,11 @@ struct Seeded {
     DevBuf d_src_solve, d_src_tsolve;  // level solves on the caller's x: source row of b per row of x
     std::map<std::pair<int, int>, std::unique_ptr<SmallProg>> small;  // key (mode, rc + 1000 * wide)
     std::map<std::pair<int, int>, std::unique_ptr<LevelProg>> level;
+    // dependency-driven regime (kernels_dep.cuh): column program of the refactorization, panel
+    // programs of the solves
+    std::unique_ptr<DepColProg> dep_col;
+    bool dep_col_tried = false;
+    std::map<int, std::unique_ptr<DepPanelProg>> dep_panel;  // key: transpose
     std::map<std::pair<int, int>, std::unique_ptr<RRKernel>> rowreg;  // key (transpose, n_rhs)
     DevBuf d_scsc;  // CSC position of every entry of the (col,row)-sorted pattern (COO map of the rowreg kernels)
     int64_t info_levels = 0, info_mac = 0, info_nbatch = 0, info_stream_words = 0;
@@ -361,6 +366,51 @@ static int get_level_prog(Symbolic* S, int cx, int mode, long long batch_cols, L
     }
     *out = it->second.get();
     return 0;
+}
+
+// Dependency-driven regime: programs are built on first use; nullptr = the pattern does not
+// qualify (the level kernels take over).
+static DepColProg* get_dep_col(Symbolic* S, int cx) {
+    Seeded& sd = S->seeded[cx];
+    if (!sd.dep_col_tried) {
+        sd.dep_col_tried = true;
+        int64_t cap = 64LL << 20;  // multiply-adds: the 16-bit destination list is 2 bytes each
+        if (const char* e = std::getenv("KLUJAX_CUDA_DEP_MAXMAC")) cap = std::atoll(e);
+        if (sd.info_mac <= cap) {
+            ColProgram cp;
+            if (build_col_program(sd.piv, sd.lay, cp) && dep_factor_plan(sd.lay.n, cp.maxcol, cx ? 16 : 8).ok) {
+                auto dp = std::make_unique<DepColProg>();
+                if (dp->upload(cp)) sd.dep_col = std::move(dp);
+                else cudaGetLastError();
+            }
+        }
+        if (std::getenv("KLUJAX_CUDA_VERBOSE"))
+            std::fprintf(stderr, "[dep] column program: %s (mac %lld)\n", sd.dep_col ? "built" : "not used", static_cast<long long>(sd.info_mac));
+    }
+    return sd.dep_col.get();
+}
+
+static DepPanelProg* get_dep_panel(Symbolic* S, int cx, bool transpose) {
+    Seeded& sd = S->seeded[cx];
+    auto it = sd.dep_panel.find(transpose ? 1 : 0);
+    if (it == sd.dep_panel.end()) {
+        std::unique_ptr<DepPanelProg> dp;
+        PanelProgram pp;
+        // the right-hand side has to fit in shared memory (checked before the program is built)
+        if (static_cast<size_t>(sd.lay.n) * (cx ? 16 : 8) < kDepSmemMax && build_panel_program(S->ord, sd.piv, sd.lay, transpose, pp) &&
+            panel_plan(sd.lay.n, pp.ntemps, pp.maxI, cx ? 16 : 8).ok) {
+            dp = std::make_unique<DepPanelProg>();
+            if (!dp->upload(pp)) {
+                cudaGetLastError();
+                dp.reset();
+            }
+        }
+        if (std::getenv("KLUJAX_CUDA_VERBOSE"))
+            std::fprintf(stderr, "[dep] panel program (transpose %d): %s, %d panels, %d temporaries, depth E %d I %d\n", int(transpose),
+                         dp ? "built" : "not used", pp.npanels, pp.ntemps, pp.maxE, pp.maxI);
+        it = sd.dep_panel.emplace(transpose ? 1 : 0, std::move(dp)).first;
+    }
+    return it->second.get();
 }
 
 // ---------------------------------------------------------------------------
@@ -759,15 +809,27 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
         lc.Lstore = op.batch->L;
     }
     LevelProg *pf = nullptr, *ps = nullptr;
+    // Batches that are not larger than the machine: the dependency-driven kernels (a CTA per
+    // system / right-hand-side column, no level barriers), if the pattern qualifies.
+    const bool dep_on = dep_enabled();
     if (factor) {
-        int e = get_level_prog(S, cx, PM_FACTOR, op.L, &pf);
-        if (e) return e;
+        // the column kernel is an experiment that did not beat the level kernel (profiles/dep_r02.md): opt-in
+        if (dep_on && dep_env_int("KLUJAX_CUDA_DEP_FACTOR", 0) && op.L <= lc.num_sms) lc.dep_col = get_dep_col(S, cx);
+        if (lc.dep_col) {
+            sd.info_levels = lc.dep_col->depth;
+        } else {
+            int e = get_level_prog(S, cx, PM_FACTOR, op.L, &pf);
+            if (e) return e;
+        }
     }
     if (op.mode != PM_FACTOR) {
         const bool tr = (op.mode == PM_FACTOR_TSOLVE || op.mode == PM_TSOLVE);
         const long long Q = static_cast<long long>(op.L) * op.r;
-        int e = get_level_prog(S, cx, tr ? PM_TSOLVE : PM_SOLVE, Q, &ps, level_native(Q, op.r, lc.num_sms));
-        if (e) return e;
+        if (dep_on && Q <= 2LL * lc.num_sms) lc.dep_panel = get_dep_panel(S, cx, tr);
+        if (!lc.dep_panel) {
+            int e = get_level_prog(S, cx, tr ? PM_TSOLVE : PM_SOLVE, Q, &ps, level_native(Q, op.r, lc.num_sms));
+            if (e) return e;
+        }
     }
     std::string err;
     int rc = level_run(lc, pf, ps, err);

@@ -825,3 +825,240 @@ bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedPro
 }
 
 }  // namespace kb
+
+// ---------------------------------------------------------------------------------------------
+// Dependency-driven regime (plan.hpp: ColProgram, RowProgram)
+// ---------------------------------------------------------------------------------------------
+namespace kb {
+
+bool build_col_program(const PivotPlan& piv, const SlotLayout& lay, ColProgram& out) {
+    const int n = lay.n;
+    out = ColProgram();
+    out.n = n;
+    out.colinfo.resize(4 * static_cast<size_t>(n));
+    out.ccand.assign(n, -2);
+    size_t nu = 0;
+    for (int k = 0; k < n; ++k) nu += static_cast<size_t>(lay.diag_slot[k] - lay.col_begin[k]);
+    out.urec.resize(4 * nu);
+    std::vector<int> pos(n, -1), depth(n, 0);
+    size_t u = 0;
+    for (int k = 0; k < n; ++k) {
+        const int cb = lay.col_begin[k], dg = lay.diag_slot[k], ce = lay.col_begin[k + 1];
+        const int nc = ce - cb;
+        if (nc > 65535) return false;  // positions inside a column are 16-bit
+        out.maxcol = std::max(out.maxcol, nc);
+        out.colinfo[4 * k + 0] = cb;
+        out.colinfo[4 * k + 1] = dg - cb;
+        out.colinfo[4 * k + 2] = nc;
+        out.colinfo[4 * k + 3] = static_cast<int>(u);
+        for (int s = cb; s < ce; ++s) pos[lay.slot_row[s]] = s - cb;
+        int d = 0;
+        for (int su = cb; su < dg; ++su, ++u) {  // ascending pivot rows: a topological order
+            const int j = lay.slot_row[su];
+            const int lbeg = lay.diag_slot[j] + 1, lcnt = lay.col_begin[j + 1] - lbeg;
+            if (out.dest.size() + static_cast<size_t>(lcnt) >= (1ull << 31)) return false;
+            out.urec[4 * u + 0] = j;
+            out.urec[4 * u + 1] = lbeg;
+            out.urec[4 * u + 2] = lcnt;
+            out.urec[4 * u + 3] = static_cast<int>(out.dest.size());
+            for (int sl = lbeg; sl < lbeg + lcnt; ++sl) {
+                const int p = pos[lay.slot_row[sl]];
+                if (p < 0) return false;  // the pattern of column k always contains L(:,j) below row j
+                out.dest.push_back(static_cast<uint16_t>(p));
+            }
+            out.n_mac += lcnt;
+            d = std::max(d, depth[j]);
+        }
+        depth[k] = d + 1;
+        out.depth = std::max(out.depth, depth[k]);
+        if (!piv.diag_cand.empty() && piv.diag_cand[k] != -2) {
+            const int c = piv.diag_cand[k];
+            out.ccand[k] = (c >= 0 && pos[c] > dg - cb) ? pos[c] : -1;
+        }
+        for (int s = cb; s < ce; ++s) pos[lay.slot_row[s]] = -1;
+    }
+    if (out.dest.empty()) out.dest.push_back(0);
+    if (out.urec.empty()) out.urec.assign(4, 0);
+    return true;
+}
+
+bool build_panel_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, bool transpose,
+                         PanelProgram& out) {
+    const int n = lay.n;
+    out = PanelProgram();
+    out.n = n;
+    struct Opnd {
+        int slot, row;  // slot -2: the constant -1
+        int wseq;       // sequence number of the task that produced the operand (-1: the loaded b)
+    };
+    struct PTask {
+        int row, div;
+        bool mul, noinit;
+        std::vector<Opnd> ops;
+    };
+    std::vector<PTask> seq;
+    std::vector<int> last_writer(n, -1);  // emission-order index of the latest task that wrote row k
+    int ntemps = 0;
+    auto emit = [&](int row, int div, bool mul, std::vector<Opnd>& ops) {
+        for (Opnd& o : ops) o.wseq = last_writer[o.row];
+        // earliest-produced operands first: they are the ones that can be summed ahead of time
+        std::stable_sort(ops.begin(), ops.end(), [](const Opnd& a, const Opnd& b) { return a.wseq < b.wseq; });
+        size_t done = 0;
+        std::vector<int> temps;
+        while (ops.size() - done > static_cast<size_t>(kPanelChunk)) {
+            PTask pt;
+            pt.row = n + ntemps;
+            pt.div = -1;
+            pt.mul = false;
+            pt.noinit = true;
+            pt.ops.assign(ops.begin() + done, ops.begin() + done + kPanelChunk);
+            done += kPanelChunk;
+            temps.push_back(n + ntemps);
+            ++ntemps;
+            seq.push_back(std::move(pt));
+        }
+        PTask t;
+        t.row = row;
+        t.div = div;
+        t.mul = mul;
+        t.noinit = false;
+        t.ops.assign(ops.begin() + done, ops.end());
+        for (int tr : temps) t.ops.push_back({-2, tr, 0});  // acc -= (-1) * partial
+        out.n_mac += static_cast<int64_t>(ops.size());
+        last_writer[row] = static_cast<int>(seq.size());
+        seq.push_back(std::move(t));
+    };
+    std::vector<Opnd> ops;
+    if (!transpose) {
+        std::vector<std::vector<std::pair<int, int>>> lrow(n), urow(n), offrow(n);
+        for (int k = 0; k < n; ++k) {
+            for (int s = lay.col_begin[k]; s < lay.diag_slot[k]; ++s) urow[lay.slot_row[s]].emplace_back(s, k);
+            for (int s = lay.diag_slot[k] + 1; s < lay.col_begin[k + 1]; ++s) lrow[lay.slot_row[s]].emplace_back(s, k);
+            for (int p = piv.Offp[k]; p < piv.Offp[k + 1]; ++p) offrow[piv.Offi[p]].emplace_back(lay.n_lu + p, k);
+        }
+        // klu_solve: blocks last -> first; L then U inside a block
+        for (int b = ord.nblocks - 1; b >= 0; --b) {
+            const int k1 = ord.R[b], k2 = ord.R[b + 1];
+            if (k2 - k1 == 1) {
+                ops.clear();
+                for (auto& e : offrow[k1]) ops.push_back({e.first, e.second, 0});
+                emit(k1, lay.diag_slot[k1], true, ops);
+                continue;
+            }
+            for (int i = k1; i < k2; ++i) {
+                if (offrow[i].empty() && lrow[i].empty()) continue;
+                ops.clear();
+                for (auto& e : offrow[i]) ops.push_back({e.first, e.second, 0});
+                for (auto& e : lrow[i]) ops.push_back({e.first, e.second, 0});
+                emit(i, -1, false, ops);
+            }
+            for (int i = k2 - 1; i >= k1; --i) {
+                ops.clear();
+                for (auto& e : urow[i]) ops.push_back({e.first, e.second, 0});
+                emit(i, lay.diag_slot[i], true, ops);
+            }
+        }
+    } else {
+        // klu_tsolve: blocks first -> last; U' then L' inside a block
+        for (int b = 0; b < ord.nblocks; ++b) {
+            const int k1 = ord.R[b], k2 = ord.R[b + 1];
+            for (int k = k1; k < k2; ++k) {
+                ops.clear();
+                for (int p = piv.Offp[k]; p < piv.Offp[k + 1]; ++p) ops.push_back({lay.n_lu + p, piv.Offi[p], 0});
+                for (int s = lay.col_begin[k]; s < lay.diag_slot[k]; ++s) ops.push_back({s, lay.slot_row[s], 0});
+                emit(k, lay.diag_slot[k], true, ops);
+            }
+            if (k2 - k1 == 1) continue;
+            for (int k = k2 - 1; k >= k1; --k) {
+                if (lay.diag_slot[k] + 1 == lay.col_begin[k + 1]) continue;
+                ops.clear();
+                for (int s = lay.diag_slot[k] + 1; s < lay.col_begin[k + 1]; ++s) ops.push_back({s, lay.slot_row[s], 0});
+                emit(k, -1, false, ops);
+            }
+        }
+    }
+    out.ntemps = ntemps;
+    const int ntask = static_cast<int>(seq.size());
+    out.npanels = (ntask + 31) / 32;
+    if (out.npanels == 0) return false;
+    out.hdr.assign(4 * static_cast<size_t>(out.npanels), 0);
+    out.lane.assign(4 * 32 * static_cast<size_t>(out.npanels), 0);
+    // classification pass: who wrote each operand last, in final numbering
+    std::vector<int> writer(n + ntemps, -1);
+    struct LaneOps {
+        std::vector<std::pair<int, int>> ext;  // (slot, row)
+        std::vector<std::pair<int, int>> in;   // (producing lane, slot)
+    };
+    std::vector<LaneOps> lo(32);
+    for (int p = 0; p < out.npanels; ++p) {
+        const int g0 = p * 32, g1 = std::min(ntask, g0 + 32);
+        int E = 0, I = 0;
+        for (int g = g0; g < g1; ++g) {
+            const PTask& t = seq[g];
+            LaneOps& l = lo[g - g0];
+            l.ext.clear();
+            l.in.clear();
+            bool noinit = t.noinit;
+            unsigned mask = 0;
+            auto classify = [&](int slot, int row) {
+                const int w = writer[row];
+                if (w >= g0) {
+                    l.in.emplace_back(w - g0, slot);
+                    mask |= 1u << (w - g0);
+                } else {
+                    l.ext.emplace_back(slot, row);
+                }
+            };
+            if (!noinit && writer[t.row] >= g0) {  // the row's own previous value was produced in this panel
+                classify(-2, t.row);
+                noinit = true;
+            }
+            for (const Opnd& o : t.ops) classify(o.slot, o.row);
+            // one operand per producing lane: two entries of a row never share a column
+            std::sort(l.in.begin(), l.in.end());
+            for (size_t q = 1; q < l.in.size(); ++q)
+                if (l.in[q].first == l.in[q - 1].first) return false;
+            E = std::max<int>(E, static_cast<int>(l.ext.size()));
+            I = std::max<int>(I, static_cast<int>(l.in.size()));
+            int* li = &out.lane[4 * static_cast<size_t>(g)];
+            li[0] = t.row;
+            li[1] = t.div;
+            li[2] = static_cast<int>(mask);
+            li[3] = (noinit ? 1 : 0) | (t.mul ? 4 : 0);
+            if (writer[t.row] >= g0) out.lane[4 * static_cast<size_t>(writer[t.row]) + 3] |= 2;  // superseded inside the panel
+            writer[t.row] = g;
+        }
+        for (int g = g1; g < g0 + 32; ++g) {  // idle lanes of the last panel
+            int* li = &out.lane[4 * static_cast<size_t>(g)];
+            li[0] = 0;
+            li[1] = -1;
+            li[2] = 0;
+            li[3] = 1 | 2;
+            lo[g - g0].ext.clear();
+            lo[g - g0].in.clear();
+        }
+        out.hdr[4 * p + 0] = E;
+        out.hdr[4 * p + 1] = I;
+        out.hdr[4 * p + 2] = static_cast<int>(out.ext_slot.size() / 32);
+        out.hdr[4 * p + 3] = static_cast<int>(out.in_slot.size() / 32);
+        out.maxE = std::max(out.maxE, E);
+        out.maxI = std::max(out.maxI, I);
+        for (int e = 0; e < E; ++e)
+            for (int ln = 0; ln < 32; ++ln) {
+                const bool has = e < static_cast<int>(lo[ln].ext.size());
+                out.ext_slot.push_back(has ? lo[ln].ext[e].first : -1);
+                out.ext_idx.push_back(has ? lo[ln].ext[e].second : -1);
+            }
+        for (int t = 0; t < I; ++t)
+            for (int ln = 0; ln < 32; ++ln)
+                out.in_slot.push_back(t < static_cast<int>(lo[ln].in.size()) ? lo[ln].in[t].second : -1);
+    }
+    if (out.ext_slot.empty()) {
+        out.ext_slot.assign(32, -1);
+        out.ext_idx.assign(32, -1);
+    }
+    if (out.in_slot.empty()) out.in_slot.assign(32, -1);
+    return true;
+}
+
+}  // namespace kb

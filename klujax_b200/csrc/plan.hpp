@@ -138,4 +138,53 @@ bool pack_program(const SlotLayout& lay, const TaskProgram& prog, PackedProgram&
 // 128 (header word, operand word) pairs, one per lane; chunk_ptr[c] = first step of chunk c; nbatch = steps
 bool pack_program_wide(const SlotLayout& lay, const TaskProgram& prog, PackedProgram& out, int elem_bytes = 16);
 
+
+// ---------------------------------------------------------------------------------------------
+// Dependency-driven regime (kernels_dep.cuh): no level barriers.  For batches that are not larger
+// than the machine a CTA owns ONE system and the level-scheduled kernels pay a CTA barrier plus a
+// memory round trip per level (cfg 4: 5 215 + 2 x 6 205 levels per step).  Here the work is dealt
+// to the warps of the CTA in a fixed sequential order and every unit waits only for the units it
+// really depends on, through ready flags in shared memory (refactorization), or runs in one
+// sequential order with the dependencies of 32 consecutive tasks resolved by warp shuffles (solves).
+//
+// ColProgram - left-looking refactorization by columns, the shape of klu_refactor's own loop
+// (/root/reference/klujax.cpp:781, 911 through KLU): a warp owns column k; for every U(j,k) in
+// topological order it waits for column j and subtracts L(:,j) * U(j,k) from the column, then
+// finishes the pivot and scales L(:,k).  The critical path is the depth of the column
+// elimination DAG (cfg 4: 2 610 columns against 5 215 entry levels).
+struct ColProgram {
+    int n = 0, maxcol = 0, depth = 0;
+    std::vector<int> colinfo;    // 4 per column: first slot, number of U entries, entries, first update record
+    std::vector<int> ccand;      // per column: -2 diagonal pivot, -1 off-diagonal pivot, else position (inside the
+                                 // column) of the diagonal candidate that failed the threshold test (plan.hpp: TK_MUL_TRACK_*)
+    std::vector<int> urec;       // 4 per U entry, in slot order: pivot column j, first slot of L(:,j), its length, offset into dest
+    std::vector<uint16_t> dest;  // per multiply-add: position of the destination inside column k
+    int64_t n_mac = 0;
+};
+bool build_col_program(const PivotPlan& piv, const SlotLayout& lay, ColProgram& out);
+
+// PanelProgram - klu_solve / klu_tsolve as ONE sequential list of row tasks (the order of
+// klu_solve's own loops), cut into panels of 32 consecutive tasks: lane r of a warp owns task r of
+// the panel.  Operands produced by earlier panels are "external" (read from the right-hand-side
+// array, which is final for them because panels run strictly one after the other: no flags),
+// operands produced by an earlier lane of the same panel are resolved inside the warp by a
+// shuffle loop over the producing lanes (kernels_dep.cuh: panel_solve).  A chain of dependent
+// rows - the shape of circuit and banded matrices - costs one shuffle step (~45 cycles) per row
+// instead of one CTA barrier and memory round trip (~950 cycles) per row.
+//   hdr       4 ints per panel: external depth E, in-panel depth I, first external line, first in-panel line
+//   lane      4 ints per task : row (>= n: temporary of a split dot product), pivot slot or -1,
+//                               mask of the producing lanes, bits (1 start from 0, 2 do not store, 4 multiply by the pivot)
+//   ext_slot / ext_idx  E lines of 32 per panel: value slot (-2 = the constant -1) and row, -1 = none
+//   in_slot             I lines of 32 per panel: value slot per producing lane, ascending (-2 = the constant -1)
+// Dot products with more than `kPanelChunk` operands are split: partial tasks (start from 0, write
+// a temporary row) run on other lanes, the final task subtracts their results.
+constexpr int kPanelChunk = 24;
+struct PanelProgram {
+    int n = 0, npanels = 0, ntemps = 0, maxI = 0, maxE = 0;
+    std::vector<int> hdr, lane, ext_slot, ext_idx, in_slot;
+    int64_t n_mac = 0;
+};
+bool build_panel_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, bool transpose,
+                         PanelProgram& out);
+
 }  // namespace kb
