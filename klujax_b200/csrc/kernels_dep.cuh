@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(1024, 1) dep_factor(const DepArgs a) {
 }
 
 // Panels of 32 row tasks, taken in turn by the warps of the CTA (see the header).
-constexpr int kPanelWarps = 4;
+constexpr int kPanelWarps = 8;
 template <typename T>
 __global__ void __launch_bounds__(32 * kPanelWarps, 1) panel_solve(const DepArgs a) {
     using S = Sc<T>;
@@ -296,6 +296,9 @@ __global__ void __launch_bounds__(32 * kPanelWarps, 1) panel_solve(const DepArgs
             if (slot == -2) v = S::sub(v, S::one());
             return v;
         };
+        long long tp[6] = {0, 0, 0, 0, 0, 0}, tc = 0;
+        const bool prof = a.prof != nullptr;
+        if (prof) tc = clock64();
         for (int p = w; p < a.npanels; p += NW) {
             // ---- static part: needs nothing from earlier panels ----
             const int4 h = __ldg(a.hdr + p);
@@ -305,6 +308,11 @@ __global__ void __launch_bounds__(32 * kPanelWarps, 1) panel_solve(const DepArgs
             V_t dv = S::one();
             if (li.y >= 0) dv = __ldg(Vs + static_cast<long long>(li.y) * ls);
             const int* isl = a.in_slot + static_cast<size_t>(h.w) * 32 + lane;
+            // In-panel coefficients, staged in shared memory.  The producing lane's pivot reciprocal is
+            // folded in here (x_s = acc_s * d_s, so acc_r -= (c * d_s) * acc_s): the shuffle loop below
+            // then carries acc itself and its dependent chain is shuffle + one multiply-add per step.
+            const V_t dve = mulp ? dv : S::one();
+            unsigned rest = static_cast<unsigned>(li.z);
             for (int t0 = 0; t0 < I; t0 += kStageB) {  // all index loads, then all value loads, then the stores
                 int sl[kStageB];
                 V_t sv[kStageB];
@@ -313,8 +321,12 @@ __global__ void __launch_bounds__(32 * kPanelWarps, 1) panel_solve(const DepArgs
 #pragma unroll
                 for (int u = 0; u < kStageB; ++u) sv[u] = coef(sl[u]);
 #pragma unroll
-                for (int u = 0; u < kStageB; ++u)
-                    if (t0 + u < I) stage[(t0 + u) * 32 + lane] = sv[u];
+                for (int u = 0; u < kStageB; ++u) {
+                    const int src = rest ? __ffs(rest) - 1 : lane;  // my (t0+u)-th producing lane
+                    rest &= rest - 1;
+                    const V_t ds = S::shfl_idx(dve, src);
+                    if (t0 + u < I) stage[(t0 + u) * 32 + lane] = S::mul(sv[u], ds);
+                }
             }
             const int* esl = a.ext_slot + static_cast<size_t>(h.z) * 32 + lane;
             const int* eix = a.ext_idx + static_cast<size_t>(h.z) * 32 + lane;
@@ -332,9 +344,11 @@ __global__ void __launch_bounds__(32 * kPanelWarps, 1) panel_solve(const DepArgs
                 for (int u = 0; u < kPanelEC; ++u) ec[u] = coef(ei[u] >= 0 ? es[u] : -1);
             };
             fetch(0);
+            DEP_TICK(0)  // static part (issue; the loads complete while the warp waits)
             // ---- my turn ----
             while (*done < p) __nanosleep(a.sleep_ns);
             __threadfence_block();
+            DEP_TICK(1)  // waiting for the turn
             V_t acc = (li.w & 1) ? S::zero() : Xs[li.x];
             for (int e0 = 0; e0 < E; e0 += kPanelEC) {
                 int ci[kPanelEC];
@@ -346,24 +360,32 @@ __global__ void __launch_bounds__(32 * kPanelWarps, 1) panel_solve(const DepArgs
                 for (int u = 0; u < kPanelEC; ++u)
                     if (ci[u] >= 0) S::fms_acc(acc, cc[u], Xs[ci[u]]);
             }
+            DEP_TICK(2)  // operands from earlier panels
             // operands produced inside the panel: one shuffle step per producing lane
             unsigned any = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(li.z));
             int t = 0;
+            const int tmax = I > 0 ? I - 1 : 0;
+            V_t cn = stage[lane];  // next coefficient of this lane, always one step ahead
             while (any) {
                 const int s = __ffs(any) - 1;
                 any &= any - 1;
-                const V_t val = mulp ? S::mul(acc, dv) : acc;
-                const V_t xs = S::shfl_idx(val, s);
-                if ((static_cast<unsigned>(li.z) >> s) & 1u) {
-                    S::fms_acc(acc, stage[t * 32 + lane], xs);
-                    ++t;
-                }
+                const V_t xs = S::shfl_idx(acc, s);
+                const bool mine = (static_cast<unsigned>(li.z) >> s) & 1u;
+                V_t c = cn;
+                if (!mine) c = S::zero();
+                S::fms_acc(acc, c, xs);
+                t += mine ? 1 : 0;
+                cn = stage[min(t, tmax) * 32 + lane];
             }
+            DEP_TICK(3)  // shuffle steps
             if (!(li.w & 2)) Xs[li.x] = mulp ? S::mul(acc, dv) : acc;
             __threadfence_block();
             __syncwarp();
             if (lane == 0) *done = p + 1;
+            DEP_TICK(4)  // store + hand-over
         }
+        if (prof && lane == 0)
+            for (int i = 0; i < 6; ++i) atomicAdd(a.prof + i, static_cast<unsigned long long>(tp[i]));
         __syncthreads();
         for (int k = threadIdx.x; k < n; k += blockDim.x) {
             const int dst = __ldg(a.perm_out + k);

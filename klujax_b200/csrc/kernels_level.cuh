@@ -103,6 +103,9 @@ struct LevelCall {
     // dependency-driven kernels (kernels_dep.cuh) instead of the level kernels, when set
     const DepColProg* dep_col = nullptr;
     const DepPanelProg* dep_panel = nullptr;
+    // per-stream scratch of the caller for the status words (no allocation on the call path when it is large enough)
+    void* aux = nullptr;
+    size_t aux_bytes = 0;
 };
 
 // scatter Ax[m][e] -> V[slot][sys]; V has been zeroed
@@ -767,12 +770,19 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
     const size_t ncnt = static_cast<size_t>(std::max<long long>(c.L, (long long)c.L * std::max(c.r, 1))) ;
     const size_t aux_bytes = 64 + sizeof(int) * (size_t)c.L + sizeof(unsigned long long) * (size_t)c.L + 64 +
                              (ncnt <= 1024 ? sizeof(unsigned) * ncnt : 0) + 64;
-    if (!chk(cudaMallocAsync(&tmpAux, aux_bytes, c.st), "alloc aux") ||
-        !chk(cudaMemsetAsync(tmpAux, 0, aux_bytes, c.st), "memset aux")) {
+    void* auxp = c.aux;
+    if (!auxp || c.aux_bytes < aux_bytes) {
+        if (!chk(cudaMallocAsync(&tmpAux, aux_bytes, c.st), "alloc aux")) {
+            cleanup();
+            return KLU_OUT_OF_MEMORY;
+        }
+        auxp = tmpAux;
+    }
+    if (!chk(cudaMemsetAsync(auxp, 0, aux_bytes, c.st), "memset aux")) {
         cleanup();
         return KLU_OUT_OF_MEMORY;
     }
-    unsigned long long* growth2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(tmpAux) + 64);
+    unsigned long long* growth2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(auxp) + 64);
     int* bad = reinterpret_cast<int*>(growth2 + c.L);
     unsigned* coop_bar = ncnt <= 1024 ? reinterpret_cast<unsigned*>(bad + ((c.L + 15) / 16) * 16) : nullptr;
 

@@ -124,6 +124,8 @@ struct Symbolic {
     // calls on different streams may overlap on the device
     struct Scratch {
         DevBuf coo_dst, coo_csc, bad;
+        DevBuf aux;  // status words of the level regime (kernels_level.cuh: level_run_t), grown on demand
+        size_t aux_bytes = 0;
     };
     std::map<cudaStream_t, std::unique_ptr<Scratch>> scratch;
     Scratch* cur = nullptr;  // scratch of the call in flight (under mu)
@@ -801,6 +803,24 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
     lc.n_val = sd.lay.n_val;
     lc.is_complex = cx;
     lc.num_sms = num_sms();
+    {
+        // bad[L], growth2[L] and the arrival counters of the cooperative kernels, per stream
+        const size_t cols = static_cast<size_t>(op.L) * static_cast<size_t>(std::max(op.r, 1));
+        const size_t need = 256 + 12 * static_cast<size_t>(op.L) + (cols <= 1024 ? 4 * cols : 0) + 64;
+        if (S->cur->aux_bytes < need) {
+            const size_t grow = std::max(need, 2 * S->cur->aux_bytes);
+            DevBuf nb;
+            if (nb.alloc(grow) == cudaSuccess) {
+                std::swap(S->cur->aux.p, nb.p);  // the old buffer is freed with nb (cudaFree waits for work in flight)
+                std::swap(S->cur->aux.bytes, nb.bytes);
+                S->cur->aux_bytes = grow;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        lc.aux = S->cur->aux.p;
+        lc.aux_bytes = S->cur->aux_bytes;
+    }
     if (op.batch) {
         lc.V = op.batch->V.p;
         lc.Rs = op.batch->Rs.as<double>();

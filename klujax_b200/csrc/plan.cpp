@@ -898,7 +898,27 @@ bool build_panel_program(const Ordering& ord, const PivotPlan& piv, const SlotLa
     };
     std::vector<PTask> seq;
     std::vector<int> last_writer(n, -1);  // emission-order index of the latest task that wrote row k
-    int ntemps = 0;
+    // Temporaries (partial sums of split dot products) come from a small ring: a partial is consumed
+    // by the final task of its row, which follows its partials immediately, and panels run one after
+    // the other - a slot is dead once the panel of that final task is done.  Two rows' worth of
+    // partials plus two panels of slack never collide.
+    long long maxops = 0;
+    if (!transpose) {
+        std::vector<long long> cnt(n, 0);
+        for (int k = 0; k < n; ++k) {
+            for (int s = lay.col_begin[k]; s < lay.diag_slot[k]; ++s) cnt[lay.slot_row[s]]++;   // U row (second pass)
+            for (int p = piv.Offp[k]; p < piv.Offp[k + 1]; ++p) cnt[piv.Offi[p]]++;
+        }
+        std::vector<long long> cl(n, 0);
+        for (int k = 0; k < n; ++k)
+            for (int s = lay.diag_slot[k] + 1; s < lay.col_begin[k + 1]; ++s) cl[lay.slot_row[s]]++;
+        for (int k = 0; k < n; ++k) maxops = std::max(maxops, cnt[k] + cl[k]);
+    } else {
+        for (int k = 0; k < n; ++k)
+            maxops = std::max<long long>(maxops, (lay.col_begin[k + 1] - lay.col_begin[k]) + (piv.Offp[k + 1] - piv.Offp[k]));
+    }
+    const int ring = static_cast<int>(((2 * (maxops / kPanelChunk + 1) + 64 + 31) / 32) * 32);
+    int ntemps = 0, temp_next = 0;
     auto emit = [&](int row, int div, bool mul, std::vector<Opnd>& ops) {
         for (Opnd& o : ops) o.wseq = last_writer[o.row];
         // earliest-produced operands first: they are the ones that can be summed ahead of time
@@ -907,14 +927,15 @@ bool build_panel_program(const Ordering& ord, const PivotPlan& piv, const SlotLa
         std::vector<int> temps;
         while (ops.size() - done > static_cast<size_t>(kPanelChunk)) {
             PTask pt;
-            pt.row = n + ntemps;
+            pt.row = n + temp_next;
             pt.div = -1;
             pt.mul = false;
             pt.noinit = true;
             pt.ops.assign(ops.begin() + done, ops.begin() + done + kPanelChunk);
             done += kPanelChunk;
-            temps.push_back(n + ntemps);
-            ++ntemps;
+            temps.push_back(n + temp_next);
+            temp_next = (temp_next + 1) % ring;
+            ntemps = std::min(ring, ntemps + 1);
             seq.push_back(std::move(pt));
         }
         PTask t;
@@ -977,7 +998,7 @@ bool build_panel_program(const Ordering& ord, const PivotPlan& piv, const SlotLa
             }
         }
     }
-    out.ntemps = ntemps;
+    out.ntemps = ntemps;  // slots of the ring in use
     const int ntask = static_cast<int>(seq.size());
     out.npanels = (ntask + 31) / 32;
     if (out.npanels == 0) return false;
