@@ -156,6 +156,15 @@ static int num_sms() {
     if (!g_num_sms[dev]) {
         cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (g_num_sms[dev] <= 0) g_num_sms[dev] = 148;
+        // first numeric call on this device: the stream-ordered scratch of the fused solves stays in the
+        // pool across synchronisations (the default threshold 0 hands it back to the driver at every
+        // sync, and the next call pays a real allocation: 20-70 ms outliers on cfg 4 / cfg 1)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
     }
     return g_num_sms[dev];
 }
