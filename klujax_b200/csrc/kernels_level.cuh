@@ -106,6 +106,7 @@ struct LevelCall {
     // per-stream scratch of the caller for the status words (no allocation on the call path when it is large enough)
     void* aux = nullptr;
     size_t aux_bytes = 0;
+    int* slot_src = nullptr;  // per-stream scratch [n_val]: inverse of coo_dst (system-major fill)
 };
 
 // scatter Ax[m][e] -> V[slot][sys]; V has been zeroed
@@ -166,14 +167,22 @@ __global__ void lv_rowscale(int L, int n, const int* __restrict__ rs_ptr,
     }
 }
 
-// System-major layout (one CTA per system): zero the fill-in slots, scatter the call's values and
-// row-scale in ONE pass over the system's own contiguous value array - every access of the zero
-// and scatter phases is coalesced along the slot axis (the three batch-interleaved kernels above
-// walk the system axis, which is the strided one in this layout: 1.44 ms per call on cfg 4).
+// System-major layout (one CTA per system): fill the system's contiguous value array and row-scale it
+// in one kernel.  The fill is a GATHER - V[slot] = Ax[entry behind the slot] or 0 - so every value is
+// written exactly once, coalesced along the slot axis; zero-then-scatter wrote the fill-in slots and
+// then hit them again with 8-byte partial writes after they had left L2 (1.0 ms per call on cfg 4,
+// 1.44 ms as three batch-interleaved kernels).  slot_src is the inverse of the call's COO map.
+__global__ void coo_invert_kernel(int nz, const int* __restrict__ coo_dst, int* __restrict__ slot_src) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nz) return;
+    const int d = coo_dst[e];
+    if (d >= 0) slot_src[d] = e;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(1024) lv_prepare_sysmajor(int L, int n, int nz, int n_val,
                                                             const typename Sc<T>::V* __restrict__ Ax, long long ax_stride,
-                                                            const int* __restrict__ coo_dst, const int* __restrict__ rs_ptr,
+                                                            const int* __restrict__ slot_src, const int* __restrict__ rs_ptr,
                                                             const int* __restrict__ rs_slot, const int* __restrict__ sysidx,
                                                             typename Sc<T>::V* __restrict__ V, double* __restrict__ Rs) {
     using S = Sc<T>;
@@ -182,21 +191,40 @@ __global__ void __launch_bounds__(1024) lv_prepare_sysmajor(int L, int n, int nz
         const long long sm = sysidx ? static_cast<long long>(sysidx[m]) : static_cast<long long>(m);
         V_t* Vs = V + sm * n_val;
         double* Rm = Rs + sm * n;
-        for (int s = threadIdx.x; s < n_val; s += blockDim.x) Vs[s] = S::zero();
-        __syncthreads();
         const V_t* Am = Ax + static_cast<long long>(m) * ax_stride;
-        for (int e = threadIdx.x; e < nz; e += blockDim.x) {
-            const int d = __ldg(coo_dst + e);
-            if (d >= 0) Vs[d] = Am[e];
+        for (int s0 = threadIdx.x; s0 < n_val; s0 += 4 * blockDim.x) {  // four independent gathers in flight
+            int e[4];
+            V_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) e[u] = s0 + u * blockDim.x < n_val ? __ldg(slot_src + s0 + u * blockDim.x) : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = e[u] >= 0 ? Am[e[u]] : S::zero();
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (s0 + u * blockDim.x < n_val) Vs[s0 + u * blockDim.x] = v[u];
         }
         __syncthreads();
+        // row scaling: the slots and the values of a row are loaded in batches of 8 (independent
+        // loads, one memory round trip each) and short rows are scaled out of registers
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const int pb = __ldg(rs_ptr + i), pe = __ldg(rs_ptr + i + 1);
+            constexpr int RB = 8;
+            int sl[RB];
+            V_t vv[RB];
+#pragma unroll
+            for (int u = 0; u < RB; ++u) sl[u] = pb + u < pe ? __ldg(rs_slot + pb + u) : -1;
+#pragma unroll
+            for (int u = 0; u < RB; ++u) vv[u] = sl[u] >= 0 ? Vs[sl[u]] : S::zero();
             double mx = 0.0;
-            for (int p = pb; p < pe; ++p) mx = fmax(mx, S::mag(Vs[__ldg(rs_slot + p)]));
+#pragma unroll
+            for (int u = 0; u < RB; ++u) mx = fmax(mx, S::mag(vv[u]));
+            for (int p = pb + RB; p < pe; ++p) mx = fmax(mx, S::mag(Vs[__ldg(rs_slot + p)]));
             if (mx == 0.0) mx = 1.0;
             Rm[i] = mx;
-            for (int p = pb; p < pe; ++p) {
+#pragma unroll
+            for (int u = 0; u < RB; ++u)
+                if (sl[u] >= 0) Vs[sl[u]] = S::rdiv(vv[u], mx);
+            for (int p = pb + RB; p < pe; ++p) {
                 V_t* q = Vs + __ldg(rs_slot + p);
                 *q = S::rdiv(*q, mx);
             }
@@ -801,9 +829,14 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
     const long long r_row = sysmajor ? 1 : lpad, r_sys = sysmajor ? c.n : 1;
     const bool factor = (pf != nullptr) || (c.dep_col != nullptr);
     if (factor) {
-        if (sysmajor && !std::getenv("KLUJAX_CUDA_NO_PREPARE")) {
+        if (sysmajor && c.slot_src && !std::getenv("KLUJAX_CUDA_NO_PREPARE")) {
+            if (!chk(cudaMemsetAsync(c.slot_src, 0xFF, sizeof(int) * static_cast<size_t>(c.n_val), c.st), "memset slot map")) {
+                cleanup();
+                return KLU_OUT_OF_MEMORY;
+            }
+            coo_invert_kernel<<<(c.nz + 255) / 256, 256, 0, c.st>>>(c.nz, c.coo_dst, c.slot_src);
             lv_prepare_sysmajor<T><<<static_cast<unsigned>(std::min<long long>(c.L, 4LL * c.num_sms)), 1024, 0, c.st>>>(
-                c.L, c.n, c.nz, c.n_val, static_cast<const V_t*>(c.Ax), c.ax_stride, c.coo_dst, c.rs_ptr, c.rs_slot, c.sysidx, V, Rs);
+                c.L, c.n, c.nz, c.n_val, static_cast<const V_t*>(c.Ax), c.ax_stride, c.slot_src, c.rs_ptr, c.rs_slot, c.sysidx, V, Rs);
         } else {
         const long long tot = (long long)c.n_val * c.L;
         const int zb = static_cast<int>(std::min<long long>((tot + 255) / 256, 148LL * 16));

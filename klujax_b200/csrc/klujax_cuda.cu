@@ -126,6 +126,7 @@ struct Symbolic {
         DevBuf coo_dst, coo_csc, bad;
         DevBuf aux;  // status words of the level regime (kernels_level.cuh: level_run_t), grown on demand
         size_t aux_bytes = 0;
+        DevBuf slot_src;  // level regime, system-major fill: COO entry behind every value slot
     };
     std::map<cudaStream_t, std::unique_ptr<Scratch>> scratch;
     Scratch* cur = nullptr;  // scratch of the call in flight (under mu)
@@ -829,6 +830,9 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
         }
         lc.aux = S->cur->aux.p;
         lc.aux_bytes = S->cur->aux_bytes;
+        if (factor && !S->cur->slot_src.p && S->cur->slot_src.alloc(sizeof(int) * (static_cast<size_t>(sd.lay.n_val) + 1)) != cudaSuccess)
+            cudaGetLastError();
+        lc.slot_src = S->cur->slot_src.as<int>();
     }
     if (op.batch) {
         lc.V = op.batch->V.p;
