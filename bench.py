@@ -172,11 +172,17 @@ def parity_sample(w: "Workload", Ax_np, b_np, x_np, n_check: int, xt_np=None) ->
 
 
 def lib_fingerprint() -> str:
+    """Fingerprint of the CUDA library's SOURCES (csrc/ + include/): what an ncu capture in profiles/ was
+    taken with.  (The binary itself is rebuilt by build() wherever the sources are newer.)"""
     import hashlib
-    from klujax_b200 import _cabi
     h = hashlib.sha256()
-    with open(_cabi.LIB_PATH, "rb") as f:
-        h.update(f.read())
+    csrc = os.path.join(ROOT, "klujax_b200", "csrc")
+    files = sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".cc", ".h")))
+    files.append(os.path.join(ROOT, "include", "klujax_cuda.h"))
+    for path in files:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
     return h.hexdigest()[:16]
 
 
@@ -363,7 +369,7 @@ def measure(K, name: str, lhs, steps: int, warmup: int, rank: int, world: int, d
             _cabi.check(f_so(symh, L, _cabi.u64p(nh), L, n, r, P(b_d), P(x_d), sp))
             _cabi.check(f_ts(symh, L, _cabi.u64p(nh), L, n, r, P(b_d), P(xt_d), sp))
         launches_per_step = 6 + 3 + 3
-        kernel = "lv_factor + lv_solve (refactor, solve, transpose solve)"
+        kernel = "lv_prepare_sysmajor + lv_factor (refactor), panel_solve (solve, transpose solve)"
     else:  # cfg3
         numeric = K.factor(Ai_d, Aj_d, Ax_d, sym)
         nh = np.ascontiguousarray(numeric.handle)

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(32 * kPanelWarps, 1) panel_solve(const DepArgs
                     const int src = rest ? __ffs(rest) - 1 : lane;  // my (t0+u)-th producing lane
                     rest &= rest - 1;
                     const V_t ds = S::shfl_idx(dve, src);
-                    if (t0 + u < I) stage[(t0 + u) * 32 + lane] = S::mul(sv[u], ds);
+                    if (t0 + u < I) stage[(t0 + u) * 32 + lane] = S::sub(S::zero(), S::mul(sv[u], ds));  // negated: the loop adds
                 }
             }
             const int* esl = a.ext_slot + static_cast<size_t>(h.z) * 32 + lane;
@@ -362,20 +362,24 @@ __global__ void __launch_bounds__(32 * kPanelWarps, 1) panel_solve(const DepArgs
             }
             DEP_TICK(2)  // operands from earlier panels
             // operands produced inside the panel: one shuffle step per producing lane
-            unsigned any = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(li.z));
+            const unsigned any = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(li.z));
             int t = 0;
             const int tmax = I > 0 ? I - 1 : 0;
-            V_t cn = stage[lane];  // next coefficient of this lane, always one step ahead
-            while (any) {
-                const int s = __ffs(any) - 1;
-                any &= any - 1;
-                const V_t xs = S::shfl_idx(acc, s);
-                const bool mine = (static_cast<unsigned>(li.z) >> s) & 1u;
-                V_t c = cn;
-                if (!mine) c = S::zero();
-                S::fms_acc(acc, c, xs);
-                t += mine ? 1 : 0;
-                cn = stage[min(t, tmax) * 32 + lane];
+            V_t cn = stage[lane];  // next (negated) coefficient of this lane, always one step ahead
+            // unrolled over the 32 possible producing lanes: the shuffle source is an immediate and a
+            // lane nobody consumes costs one uniform branch (a loop over the set bits put a
+            // find-first-set in front of every shuffle: ~100 cycles per step instead of ~45)
+#pragma unroll
+            for (int s = 0; s < 31; ++s) {
+                if (any & (1u << s)) {
+                    const V_t xs = S::shfl_idx(acc, s);
+                    const bool mine = (static_cast<unsigned>(li.z) >> s) & 1u;
+                    V_t c = cn;
+                    if (!mine) c = S::zero();
+                    S::fma_acc(acc, c, xs);
+                    t += mine ? 1 : 0;
+                    cn = stage[min(t, tmax) * 32 + lane];
+                }
             }
             DEP_TICK(3)  // shuffle steps
             if (!(li.w & 2)) Xs[li.x] = mulp ? S::mul(acc, dv) : acc;
