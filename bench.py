@@ -437,10 +437,10 @@ def measure(K, name: str, lhs, steps: int, warmup: int, rank: int, world: int, d
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
                 "kernel": f"{kernel} (whole step timed with CUDA events; the COO map and status kernels are "
-                          "<1% of it per profiles/launches_r01.csv)",
+                          "~2% of it per profiles/launches_cfg5_r02.csv)",
                 "algorithmic_bytes_per_system": per_sys}
     if w.name == "cfg5":  # what actually binds (ncu, profiles/README.md): on-chip, not HBM
-        roofline["binding_resource"] = ("shared-memory wavefronts ~67% of peak and issue slots ~51% busy "
+        roofline["binding_resource"] = ("shared-memory wavefronts ~68% of peak and issue slots ~51% busy "
                                         "(ncu --set full, profiles/): the on-chip pipes of the SM with six "
                                         "resident systems, not HBM")
     tr = os.path.join(ROOT, "profiles", "traffic.json")
