@@ -103,6 +103,7 @@ struct LevelCall {
     // dependency-driven kernels (kernels_dep.cuh) instead of the level kernels, when set
     const DepColProg* dep_col = nullptr;
     const DepPanelProg* dep_panel = nullptr;
+    const struct GroupProg* grp = nullptr;  // multi-right-hand-side solve with register blocking over rows
     // per-stream scratch of the caller for the status words (no allocation on the call path when it is large enough)
     void* aux = nullptr;
     size_t aux_bytes = 0;
@@ -599,6 +600,228 @@ __global__ void __launch_bounds__(C >= 8 ? 768 : 1024) lv_solve(const LvArgs a) 
     }
 }
 
+// ---- multi-right-hand-side solves with register blocking over rows (plan.hpp: GroupProgram) ----
+struct GroupProg {
+    int n = 0, ngroups = 0, nlevels = 0;
+    int64_t n_mac = 0, n_ksteps = 0;
+    int4 *d_ghdr = nullptr, *d_krec = nullptr;
+    int *d_gaux = nullptr, *d_level_ptr = nullptr;
+    ~GroupProg() {
+        if (d_ghdr) cudaFree(d_ghdr);
+        if (d_krec) cudaFree(d_krec);
+        if (d_gaux) cudaFree(d_gaux);
+        if (d_level_ptr) cudaFree(d_level_ptr);
+    }
+    bool upload(const GroupProgram& gp) {
+        n = gp.n;
+        ngroups = gp.ngroups;
+        nlevels = gp.nlevels;
+        n_mac = gp.n_mac;
+        n_ksteps = gp.n_ksteps;
+        auto up = [&](void** d, const std::vector<int>& v) {
+            if (cudaMalloc(d, std::max<size_t>(v.size() * sizeof(int), 16)) != cudaSuccess) return false;
+            return v.empty() || cudaMemcpy(*d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+        };
+        return up(reinterpret_cast<void**>(&d_ghdr), gp.ghdr) && up(reinterpret_cast<void**>(&d_krec), gp.krec) &&
+               up(reinterpret_cast<void**>(&d_gaux), gp.gaux) && up(reinterpret_cast<void**>(&d_level_ptr), gp.level_ptr);
+    }
+};
+
+constexpr int kGroupKC = 16;  // k-steps staged per chunk
+template <typename V_t, int C>
+constexpr size_t grouped_warp_bytes() {
+    return (static_cast<size_t>(kGroupKC) * 32 * C + static_cast<size_t>(kGroupKC) * kGroupRows + 36) * sizeof(V_t) +
+           static_cast<size_t>(kGroupKC) * 12 * sizeof(int);
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+
+struct GrpArgs {
+    const int4* ghdr;
+    const int4* krec;   // 3 per k-step
+    const int* gaux;    // kGroupAux per group
+    const int* level_ptr;
+    int nlevels, n, r;
+    long long Q, lpad, vss, xss, b_stride, rlp, rss;
+    const void* V;
+    void* X;
+    const void* B;
+    const int* sysidx;
+    const int* src_of;
+    const double* Rs;
+    int scale_in, scale_out;
+};
+
+// A CTA owns 32*C adjacent right-hand-side columns of ONE system (C divides r, 32*C divides r or the
+// tail lanes idle); a warp is one group task: lane = C adjacent columns, the accumulators of the up to
+// 8 rows of the group live in registers, a row of X is read once per k-step and applied to every row
+// of the group that has an entry there (warp-uniform branches: the slots are the same for all lanes).
+// The k-loop is software-pipelined: the loads of step k+1 (row of X, up to 8 entries of L / U) are in
+// flight while step k is applied, the record of step k+2 while those are issued.
+template <typename T, int C>
+__global__ void __launch_bounds__(C * sizeof(typename Sc<T>::V) >= 32 ? 320 : 640) lv_solve_grouped(const GrpArgs a) {
+    using S = Sc<T>;
+    using V_t = typename S::V;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, NW = blockDim.x >> 5;
+    constexpr int KC = kGroupKC;
+    extern __shared__ __align__(16) unsigned char grp_smem[];
+    constexpr size_t kWarpBytes = grouped_warp_bytes<V_t, C>();
+    unsigned char* wbase = grp_smem + static_cast<size_t>(w) * kWarpBytes;
+    V_t* sx = reinterpret_cast<V_t*>(wbase);                                         // [KC][32 * C]
+    V_t* scf = sx + KC * 32 * C;                                                      // [KC][8]
+    V_t* sin = scf + KC * kGroupRows;                                                 // [36]: pivots [8], in-group entries [28]
+    int* srec = reinterpret_cast<int*>(sin + 36);                                     // [KC][12]
+    const int cols_per_cta = 32 * C;
+    const long long slices_per_sys = (a.r + cols_per_cta - 1) / cols_per_cta;
+    const long long nslices = static_cast<long long>(a.Q / a.r) * slices_per_sys;
+    for (long long sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        const int m0 = static_cast<int>(sl / slices_per_sys);
+        const int c0 = static_cast<int>(sl - static_cast<long long>(m0) * slices_per_sys) * cols_per_cta + lane * C;
+        const bool ok = c0 < a.r;  // r is a multiple of C: all C columns or none
+        const long long sm = a.sysidx ? static_cast<long long>(a.sysidx[m0]) : static_cast<long long>(m0);
+        const V_t* vb = static_cast<const V_t*>(a.V) + sm * a.vss;
+        V_t* xb = static_cast<V_t*>(a.X) + static_cast<long long>(m0) * a.xss + (ok ? c0 : 0);
+        const V_t* bb = static_cast<const V_t*>(a.B) + static_cast<long long>(m0) * a.b_stride + (ok ? c0 : 0);
+        auto xp = [&](int row) { return xb + static_cast<long long>(row) * a.r; };
+        auto vp = [&](int slot) { return vb + static_cast<long long>(slot) * a.lpad; };
+        if (ok)
+            for (int row = w; row < a.n; row += NW) {
+                const int src = __ldg(a.src_of + row);
+                V_t v[C];
+                ld_cols<V_t, C>(bb + static_cast<long long>(src) * a.r, v);
+                if (a.scale_in) {
+                    const double sc = a.Rs[static_cast<long long>(src) * a.rlp + sm * a.rss];
+#pragma unroll
+                    for (int j = 0; j < C; ++j) v[j] = S::rdiv(v[j], sc);
+                }
+                st_cols<V_t, C>(xp(row), v);
+            }
+        __syncthreads();
+        int te = __ldg(a.level_ptr);
+        for (int l = 0; l < a.nlevels; ++l) {
+            const int tb = te;
+            te = __ldg(a.level_ptr + l + 1);
+            if (ok)
+                for (int t = tb + w; t < te; t += NW) {
+                    const int4 h = __ldg(a.ghdr + t);
+                    const int nk = h.x, nt = h.z & 255, mulbits = (h.z >> 8) & 255;
+                    const bool partial = (h.z >> 30) & 1;
+                    const int4* kr = a.krec + 3 * static_cast<long long>(h.y);
+                    const int* aux = a.gaux + static_cast<long long>(kGroupAux) * h.w;
+                    int rows[kGroupRows];
+#pragma unroll
+                    for (int i = 0; i < kGroupRows; i += 4) {
+                        const int4 q = __ldg(reinterpret_cast<const int4*>(aux + i));
+                        rows[i] = q.x, rows[i + 1] = q.y, rows[i + 2] = q.z, rows[i + 3] = q.w;
+                    }
+                    V_t acc[kGroupRows][C];
+#pragma unroll
+                    for (int i = 0; i < kGroupRows; ++i) {
+                        if (i < nt) ld_cols<V_t, C>(xp(rows[i]), acc[i]);
+                    }
+                    if (!partial) {  // pivots and in-group entries of the final task: in flight with the first chunk
+                        __syncwarp();
+                        for (int q = lane; q < 36; q += 32) {
+                            const int sl1 = __ldg(aux + 8 + q);
+                            if (sl1 >= 0) {
+                                if constexpr (sizeof(V_t) == 16) cp_async<16>(sin + q, vp(sl1));
+                                else cp_async<8>(sin + q, vp(sl1));
+                            } else {
+                                sin[q] = q < 8 ? S::one() : S::zero();
+                            }
+                        }
+                        if (nk == 0) {
+                            asm volatile("cp.async.wait_all;" ::: "memory");
+                            __syncwarp();
+                        }
+                    }
+                    // k-steps in chunks of KC through the warp's shared-memory staging area: the records
+                    // (coalesced), then ALL rows of X and entries of L / U of the chunk with cp.async - one
+                    // memory round trip per chunk instead of one per k-step
+                    for (int k0 = 0; k0 < nk; k0 += KC) {
+                        const int kc = min(KC, nk - k0);
+                        __syncwarp();
+                        for (int q = lane; q < 3 * kc; q += 32) reinterpret_cast<int4*>(srec)[q] = __ldg(kr + 3 * k0 + q);
+                        __syncwarp();
+                        for (int k = 0; k < kc; ++k) {
+                            const V_t* src = xp(srec[12 * k]);
+                            V_t* dst = sx + (k * 32 + lane) * C;
+                            if constexpr (C * sizeof(V_t) % 16 == 0) {
+#pragma unroll
+                                for (int q = 0; q < static_cast<int>(C * sizeof(V_t) / 16); ++q)
+                                    cp_async<16>(reinterpret_cast<char*>(dst) + 16 * q, reinterpret_cast<const char*>(src) + 16 * q);
+                            } else {
+                                cp_async<8>(dst, src);
+                            }
+                        }
+                        for (int q = lane; q < kGroupRows * kc; q += 32) {
+                            const int sl1 = srec[12 * (q >> 3) + 1 + (q & 7)];
+                            if (sl1 >= 0) {
+                                if constexpr (sizeof(V_t) == 16) cp_async<16>(scf + q, vp(sl1));
+                                else cp_async<8>(scf + q, vp(sl1));
+                            }
+                        }
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                        __syncwarp();
+                        for (int k = 0; k < kc; ++k) {
+                            const int mask = srec[12 * k + 9];
+                            V_t xv[C];
+                            ld_cols<V_t, C>(sx + (k * 32 + lane) * C, xv);
+#pragma unroll
+                            for (int i = 0; i < kGroupRows; ++i)
+                                if (mask & (1 << i)) {
+                                    const V_t cfi = scf[k * kGroupRows + i];
+#pragma unroll
+                                    for (int j = 0; j < C; ++j) S::fms_acc(acc[i][j], cfi, xv[j]);
+                                }
+                        }
+                    }
+                    if (partial) {  // a chunk of the group's k-steps applied early: X[rows] -= sum, in place
+#pragma unroll
+                        for (int i = 0; i < kGroupRows; ++i)
+                            if (i < nt) st_cols<V_t, C>(xp(rows[i]), acc[i]);
+                        continue;
+                    }
+                    // rows of the group, in order: finish, store, feed the later rows of the group
+#pragma unroll
+                    for (int i = 0; i < kGroupRows; ++i) {
+                        if (i < nt) {
+                            if ((mulbits >> i) & 1) {
+                                const V_t dv = sin[i];
+#pragma unroll
+                                for (int j = 0; j < C; ++j) acc[i][j] = S::mul(acc[i][j], dv);
+                            }
+                            st_cols<V_t, C>(xp(rows[i]), acc[i]);
+#pragma unroll
+                            for (int jr = i + 1; jr < kGroupRows; ++jr) {
+                                if (jr < nt) {
+                                    const V_t lu = sin[8 + jr * (jr - 1) / 2 + i];  // 0 where row jr has no entry at row i
+#pragma unroll
+                                    for (int j = 0; j < C; ++j) S::fms_acc(acc[jr][j], lu, acc[i][j]);
+                                }
+                            }
+                        }
+                    }
+                }
+            __syncthreads();
+        }
+        if (a.scale_out && ok) {
+            for (int row = w; row < a.n; row += NW) {
+                const double sc = a.Rs[static_cast<long long>(row) * a.rlp + sm * a.rss];
+                V_t v[C];
+                ld_cols<V_t, C>(xp(row), v);
+#pragma unroll
+                for (int j = 0; j < C; ++j) v[j] = S::rdiv(v[j], sc);
+                st_cols<V_t, C>(xp(row), v);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // native layout for the cooperative solve (several CTAs per column: the prologue cannot live in
 // the kernel without one more group barrier): x[m][j][c] = b[m][src_of[j]][c] (/ Rs), and the
 // scaling of the transpose solve on the way out
@@ -905,6 +1128,36 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
             cleanup();
             return KLU_OUT_OF_MEMORY;
         }
+    } else if (c.grp) {
+        const bool tr = (c.mode == PM_FACTOR_TSOLVE || c.mode == PM_TSOLVE);
+        GrpArgs g = {};
+        g.ghdr = c.grp->d_ghdr; g.krec = c.grp->d_krec; g.gaux = c.grp->d_gaux; g.level_ptr = c.grp->d_level_ptr;
+        g.nlevels = c.grp->nlevels; g.n = c.n; g.r = c.r; g.Q = (long long)c.L * c.r; g.lpad = v_slot; g.vss = v_sys;
+        g.xss = (long long)c.n * c.r; g.b_stride = c.b_stride; g.rlp = r_row; g.rss = r_sys;
+        g.V = V; g.X = c.x; g.B = c.b; g.sysidx = c.sysidx; g.src_of = tr ? c.src_tsolve : c.src_solve; g.Rs = Rs;
+        g.scale_in = tr ? 0 : 1; g.scale_out = tr ? 1 : 0;
+        // two columns per lane: 10 warps x 96 registers and 99 KB of staging per CTA, two CTAs per SM - the 256
+        // slices of cfg 3 run in ONE wave (four columns per lane: 128 CTAs of 10 warps, 68 ms against 49)
+        int C = c.r % 2 == 0 ? 2 : 1;
+        if (const char* e = std::getenv("KLUJAX_CUDA_GROUP_C")) {
+            const int want = std::atoi(e);
+            if ((want == 1 || want == 2 || (want == 4 && !c.is_complex)) && c.r % want == 0) C = want;
+        }
+        const long long nsl = (long long)c.L * ((c.r + 32 * C - 1) / (32 * C));
+        const int grid = static_cast<int>(std::min<long long>(nsl, 1 << 20));
+        const int thmax = C * sizeof(V_t) >= 32 ? 320 : 640;
+        const int th = std::min(thmax, std::max(32, dep_env_int("KLUJAX_CUDA_GROUP_THREADS", 320) / 32 * 32));
+        auto launch_grouped = [&](auto kernel, size_t warp_bytes) {
+            const size_t smem = warp_bytes * static_cast<size_t>(th / 32);
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kDepSmemMax));
+            kernel<<<grid, th, smem, c.st>>>(g);
+        };
+        if (C == 4)
+            launch_grouped(lv_solve_grouped<double, 4>, grouped_warp_bytes<double, 4>());
+        else if (C == 2)
+            launch_grouped(lv_solve_grouped<T, 2>, grouped_warp_bytes<V_t, 2>());
+        else
+            launch_grouped(lv_solve_grouped<T, 1>, grouped_warp_bytes<V_t, 1>());
     } else if (ps) {
         const bool tr = (c.mode == PM_FACTOR_TSOLVE || c.mode == PM_TSOLVE);
         const long long Q = (long long)c.L * c.r;

@@ -109,6 +109,7 @@ struct Seeded {
     std::unique_ptr<DepColProg> dep_col;
     bool dep_col_tried = false;
     std::map<int, std::unique_ptr<DepPanelProg>> dep_panel;  // key: transpose
+    std::map<int, std::unique_ptr<GroupProg>> grp;            // key: transpose (multi-right-hand-side solves)
     std::map<std::pair<int, int>, std::unique_ptr<RRKernel>> rowreg;  // key (transpose, n_rhs)
     DevBuf d_scsc;  // CSC position of every entry of the (col,row)-sorted pattern (COO map of the rowreg kernels)
     int64_t info_levels = 0, info_mac = 0, info_nbatch = 0, info_stream_words = 0;
@@ -421,6 +422,28 @@ static DepPanelProg* get_dep_panel(Symbolic* S, int cx, bool transpose) {
             std::fprintf(stderr, "[dep] panel program (transpose %d): %s, %d panels, %d temporaries, depth E %d I %d\n", int(transpose),
                          dp ? "built" : "not used", pp.npanels, pp.ntemps, pp.maxE, pp.maxI);
         it = sd.dep_panel.emplace(transpose ? 1 : 0, std::move(dp)).first;
+    }
+    return it->second.get();
+}
+
+static GroupProg* get_group_prog(Symbolic* S, int cx, bool transpose) {
+    Seeded& sd = S->seeded[cx];
+    auto it = sd.grp.find(transpose ? 1 : 0);
+    if (it == sd.grp.end()) {
+        std::unique_ptr<GroupProg> gp;
+        GroupProgram hp;
+        // rows carry the names of their final positions in the caller's x (the solve runs on it)
+        if (build_group_program(S->ord, sd.piv, sd.lay, transpose, transpose ? sd.piv.Pnum.data() : S->ord.Q.data(), hp)) {
+            gp = std::make_unique<GroupProg>();
+            if (!gp->upload(hp)) {
+                cudaGetLastError();
+                gp.reset();
+            }
+        }
+        if (std::getenv("KLUJAX_CUDA_VERBOSE"))
+            std::fprintf(stderr, "[level] group program (transpose %d): %s, %d groups, %d levels, %.2f rows per read of X\n", int(transpose),
+                         gp ? "built" : "not used", hp.ngroups, hp.nlevels, hp.n_ksteps ? double(hp.n_mac) / double(hp.n_ksteps) : 0.0);
+        it = sd.grp.emplace(transpose ? 1 : 0, std::move(gp)).first;
     }
     return it->second.get();
 }
@@ -859,7 +882,10 @@ static int run_numeric(Symbolic* S, int cx, const Op& op) {
         const bool tr = (op.mode == PM_FACTOR_TSOLVE || op.mode == PM_TSOLVE);
         const long long Q = static_cast<long long>(op.L) * op.r;
         if (dep_on && Q <= 2LL * lc.num_sms) lc.dep_panel = get_dep_panel(S, cx, tr);
-        if (!lc.dep_panel) {
+        // many right-hand-side columns per system: the row-blocked solve on the caller's x
+        if (!lc.dep_panel && dep_env_int("KLUJAX_CUDA_GROUPED", 1) && op.r >= 16 && Q >= 2048 && level_native(Q, op.r, lc.num_sms))
+            lc.grp = get_group_prog(S, cx, tr);
+        if (!lc.dep_panel && !lc.grp) {
             int e = get_level_prog(S, cx, tr ? PM_TSOLVE : PM_SOLVE, Q, &ps, level_native(Q, op.r, lc.num_sms));
             if (e) return e;
         }

@@ -1083,3 +1083,211 @@ bool build_panel_program(const Ordering& ord, const PivotPlan& piv, const SlotLa
 }
 
 }  // namespace kb
+
+namespace kb {
+
+bool build_group_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, bool transpose,
+                         const int* xrow, GroupProgram& out) {
+    const int n = lay.n;
+    out = GroupProgram();
+    out.n = n;
+    auto name = [&](int k) { return xrow ? xrow[k] : k; };
+    struct RTask {
+        int row, div;
+        bool mul;
+        std::vector<std::pair<int, int>> ops;  // (value slot, operand row), pivot-order rows
+    };
+    std::vector<RTask> seq;
+    auto emit = [&](int row, int div, bool mul, std::vector<std::pair<int, int>>& ops) {
+        RTask t;
+        t.row = row;
+        t.div = div;
+        t.mul = mul;
+        t.ops = ops;
+        out.n_mac += static_cast<int64_t>(ops.size());
+        seq.push_back(std::move(t));
+    };
+    std::vector<std::pair<int, int>> ops;
+    if (!transpose) {
+        std::vector<std::vector<std::pair<int, int>>> lrow(n), urow(n), offrow(n);
+        for (int k = 0; k < n; ++k) {
+            for (int s = lay.col_begin[k]; s < lay.diag_slot[k]; ++s) urow[lay.slot_row[s]].emplace_back(s, k);
+            for (int s = lay.diag_slot[k] + 1; s < lay.col_begin[k + 1]; ++s) lrow[lay.slot_row[s]].emplace_back(s, k);
+            for (int p = piv.Offp[k]; p < piv.Offp[k + 1]; ++p) offrow[piv.Offi[p]].emplace_back(lay.n_lu + p, k);
+        }
+        for (int b = ord.nblocks - 1; b >= 0; --b) {  // klu_solve: blocks last -> first; L then U inside a block
+            const int k1 = ord.R[b], k2 = ord.R[b + 1];
+            if (k2 - k1 == 1) {
+                ops = offrow[k1];
+                emit(k1, lay.diag_slot[k1], true, ops);
+                continue;
+            }
+            for (int i = k1; i < k2; ++i) {
+                if (offrow[i].empty() && lrow[i].empty()) continue;
+                ops = offrow[i];
+                ops.insert(ops.end(), lrow[i].begin(), lrow[i].end());
+                emit(i, -1, false, ops);
+            }
+            for (int i = k2 - 1; i >= k1; --i) {
+                ops = urow[i];
+                emit(i, lay.diag_slot[i], true, ops);
+            }
+        }
+    } else {
+        for (int b = 0; b < ord.nblocks; ++b) {  // klu_tsolve: blocks first -> last; U' then L' inside a block
+            const int k1 = ord.R[b], k2 = ord.R[b + 1];
+            for (int k = k1; k < k2; ++k) {
+                ops.clear();
+                for (int p = piv.Offp[k]; p < piv.Offp[k + 1]; ++p) ops.emplace_back(lay.n_lu + p, piv.Offi[p]);
+                for (int s = lay.col_begin[k]; s < lay.diag_slot[k]; ++s) ops.emplace_back(s, lay.slot_row[s]);
+                emit(k, lay.diag_slot[k], true, ops);
+            }
+            if (k2 - k1 == 1) continue;
+            for (int k = k2 - 1; k >= k1; --k) {
+                if (lay.diag_slot[k] + 1 == lay.col_begin[k + 1]) continue;
+                ops.clear();
+                for (int s = lay.diag_slot[k] + 1; s < lay.col_begin[k + 1]; ++s) ops.emplace_back(s, lay.slot_row[s]);
+                emit(k, -1, false, ops);
+            }
+        }
+    }
+    // ---- grouping: consecutive tasks that depend on a member of the group or share operands with it
+    struct Grp {
+        std::vector<int> tasks;
+        int level = 0;
+        std::vector<int> aux, krec;
+        int nk = 0;
+    };
+    std::vector<Grp> groups;
+    {
+        std::vector<int> stamp(n, -1);  // operand rows of the current group (stamp = group id)
+        std::vector<int> member(n, -1);  // rows written by the current group
+        int gid = -1;
+        for (int t = 0; t < static_cast<int>(seq.size()); ++t) {
+            const RTask& rt = seq[t];
+            bool join = false;
+            // a group neither writes a row twice nor writes a row one of its members reads from outside
+            // (the partial tasks update the group's rows in place while its k-steps are still being read)
+            if (gid >= 0 && static_cast<int>(groups[gid].tasks.size()) < kGroupRows && member[rt.row] != gid && stamp[rt.row] != gid) {
+                int shared = 0, dep = 0;
+                for (const auto& o : rt.ops) {
+                    if (stamp[o.second] == gid) ++shared;
+                    if (member[o.second] == gid) ++dep;
+                }
+                join = dep > 0 || (!rt.ops.empty() && 2 * shared >= static_cast<int>(rt.ops.size()));
+            }
+            if (!join) {
+                groups.emplace_back();
+                gid = static_cast<int>(groups.size()) - 1;
+            }
+            groups[gid].tasks.push_back(t);
+            member[rt.row] = gid;
+            for (const auto& o : rt.ops) stamp[o.second] = gid;
+        }
+    }
+    // ---- records + levels (dependencies and anti-dependencies on the rows of X, which is updated in place).
+    // The k-steps of a group are sorted by the level at which their operand row becomes final and cut
+    // into chunks of kGroupChunk: every chunk but the last is a PARTIAL task (X[rows] -= sum, in place)
+    // that runs as early as its operands allow, on whatever warp is free - without this the thousands
+    // of k-steps of a top-separator group would all sit on the critical path of one warp.
+    constexpr int kGroupChunk = 64;
+    struct Entry {
+        int level, nk, koff, z, aux;
+    };
+    std::vector<Entry> entries;
+    std::vector<int> lw(n, 0), lr(n, 0), pos_in_group(n, -1), kidx(n, -1);
+    std::vector<int> gkrec, order_k;
+    for (size_t g = 0; g < groups.size(); ++g) {
+        Grp& G = groups[g];
+        const int nt = static_cast<int>(G.tasks.size());
+        G.aux.assign(kGroupAux, -1);
+        for (int i = 0; i < nt; ++i) pos_in_group[seq[G.tasks[i]].row] = i;
+        std::vector<int> krows;
+        gkrec.clear();
+        int base = 0, mulbits = 0;
+        for (int i = 0; i < nt; ++i) {
+            const RTask& rt = seq[G.tasks[i]];
+            G.aux[i] = name(rt.row);
+            G.aux[8 + i] = rt.mul ? rt.div : -1;
+            if (rt.mul) mulbits |= 1 << i;
+            base = std::max(base, std::max(lw[rt.row], lr[rt.row]));
+            for (const auto& o : rt.ops) {
+                const int pj = pos_in_group[o.second];
+                if (pj >= 0 && pj < i) {  // produced by an earlier row of this group
+                    G.aux[16 + i * (i - 1) / 2 + pj] = o.first;
+                } else {
+                    if (pj >= 0) return false;  // would read a row the group is updating in place (excluded by the grouping)
+                    if (kidx[o.second] < 0) {
+                        kidx[o.second] = static_cast<int>(krows.size());
+                        krows.push_back(o.second);
+                        gkrec.resize(gkrec.size() + 12, -1);
+                        gkrec[12 * kidx[o.second]] = name(o.second);
+                    }
+                    gkrec[12 * kidx[o.second] + 1 + i] = o.first;
+                }
+            }
+        }
+        const int nk = static_cast<int>(krows.size());
+        order_k.resize(nk);
+        for (int q = 0; q < nk; ++q) order_k[q] = q;
+        std::stable_sort(order_k.begin(), order_k.end(), [&](int x, int y) { return lw[krows[x]] < lw[krows[y]]; });
+        const int aux_index = static_cast<int>(out.gaux.size() / kGroupAux);
+        out.gaux.insert(out.gaux.end(), G.aux.begin(), G.aux.end());
+        int prev = base, q0 = 0;
+        const int nchunks = std::max(1, (nk + kGroupChunk - 1) / kGroupChunk);
+        for (int c = 0; c < nchunks; ++c) {
+            const int q1 = std::min(nk, q0 + kGroupChunk);
+            const bool last = c == nchunks - 1;
+            int lvl = prev;
+            for (int q = q0; q < q1; ++q) lvl = std::max(lvl, lw[krows[order_k[q]]]);
+            lvl += 1;
+            Entry e;
+            e.level = lvl;
+            e.nk = q1 - q0;
+            e.koff = static_cast<int>(out.krec.size() / 12);
+            e.z = nt | (last ? (mulbits << 8) : (1 << 30));
+            e.aux = aux_index;
+            for (int q = q0; q < q1; ++q) {
+                int* src = &gkrec[12 * order_k[q]];
+                int mask = 0;
+                for (int i = 0; i < kGroupRows; ++i)
+                    if (src[1 + i] >= 0) mask |= 1 << i;
+                src[9] = mask;  // rows of the group that have an entry at this k-step
+                out.krec.insert(out.krec.end(), src, src + 12);
+                lr[krows[order_k[q]]] = std::max(lr[krows[order_k[q]]], lvl);
+            }
+            entries.push_back(e);
+            out.n_ksteps += e.nk;
+            prev = lvl;
+            q0 = q1;
+        }
+        for (int r2 : krows) kidx[r2] = -1;
+        for (int i = 0; i < nt; ++i) {
+            const int row = seq[G.tasks[i]].row;
+            lw[row] = prev;
+            lr[row] = 0;
+            pos_in_group[row] = -1;
+        }
+        out.nlevels = std::max(out.nlevels, prev);
+    }
+    // sort by level, emit
+    std::vector<int> order(entries.size());
+    for (size_t g = 0; g < entries.size(); ++g) order[g] = static_cast<int>(g);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return entries[a].level < entries[b].level; });
+    out.ngroups = static_cast<int>(entries.size());
+    out.level_ptr.assign(out.nlevels + 1, 0);
+    for (const Entry& e : entries) out.level_ptr[e.level]++;
+    for (int l = 0; l < out.nlevels; ++l) out.level_ptr[l + 1] += out.level_ptr[l];
+    out.ghdr.reserve(4 * entries.size());
+    for (int g : order) {
+        const Entry& e = entries[g];
+        out.ghdr.push_back(e.nk);
+        out.ghdr.push_back(e.koff);
+        out.ghdr.push_back(e.z);
+        out.ghdr.push_back(e.aux);
+    }
+    if (out.krec.empty()) out.krec.assign(12, -1);
+    return out.ngroups > 0;
+}
+
+}  // namespace kb

@@ -187,4 +187,30 @@ struct PanelProgram {
 bool build_panel_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, bool transpose,
                          PanelProgram& out);
 
+
+// GroupProgram - the multi-right-hand-side solves with register blocking over rows (kernels_level.cuh:
+// lv_solve_grouped).  The level kernel reads a row of X per entry of L / U (cfg 3: 508 GB of L2 / HBM
+// traffic per step against 19 GB algorithmic).  Here up to kGroupRows consecutive row tasks of
+// klu_solve's / klu_tsolve's own order form a group when they share operands (the rows of a supernode
+// do): a thread owns a few right-hand-side columns and keeps the accumulators of ALL rows of the group
+// in registers, so a row of X is read ONCE per group ("k-step") and applied to every row that has an
+// entry there; dependencies between rows of one group are resolved thread-locally (every thread
+// has all rows of its own columns).  Groups are levelled like tasks (fewer, wider levels: a chain of
+// rows inside a supernode collapses into its groups).
+//   ghdr  4 ints per task (sorted by level): k-steps, first k-step, rows | multiply bits << 8 (bit 30: a PARTIAL
+//         task - X[rows] -= sum over its chunk of k-steps, nothing else), index of aux
+//   gaux  kGroupAux ints per group: row names [8], pivot slots [8] (-1 none), in-group slots [28]
+//         (row j <- row i at j*(j-1)/2 + i, -1 none; -2: row j continues row i, coefficient -1)
+//   krec  12 ints per k-step: row name of the operand, value slot per row of the group [8] (-1 none), mask of
+//         the rows that have an entry, 2 pad
+constexpr int kGroupRows = 8, kGroupAux = 44;
+struct GroupProgram {
+    int n = 0, ngroups = 0, nlevels = 0;
+    std::vector<int> ghdr, gaux, krec, level_ptr;
+    int64_t n_mac = 0, n_ksteps = 0;
+};
+// xrow (optional): name of pivot-order row k (its position in the caller's x); identity if null
+bool build_group_program(const Ordering& ord, const PivotPlan& piv, const SlotLayout& lay, bool transpose,
+                         const int* xrow, GroupProgram& out);
+
 }  // namespace kb

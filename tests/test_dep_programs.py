@@ -1,4 +1,5 @@
-"""Dependency-driven regime (plan.hpp: ColProgram, PanelProgram; kernels_dep.cuh).
+"""Dependency-driven regime (plan.hpp: ColProgram, PanelProgram; kernels_dep.cuh) and the row-blocked
+multi-right-hand-side solve (plan.hpp: GroupProgram; kernels_level.cuh: lv_solve_grouped).
 
 CPU part: tools/dep_check.cpp interprets both programs the way the kernels do on one system of
 several patterns (BTF blocks with off-diagonal entries, chains, dense fill, rows long enough to
@@ -62,6 +63,7 @@ def test_programs_on_the_host(dep_check, tmp_path, name):
     res = subprocess.run([dep_check, str(f)], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "order violations 0" in res.stdout and res.stdout.strip().endswith("OK"), res.stdout
+    assert res.stdout.count("group program") == 2 and "level snapshot" in res.stdout, res.stdout
 
 
 # --------------------------------------------------------------------------------------- GPU
@@ -130,3 +132,41 @@ def test_panel_solve_reports_singular_and_keeps_status(K, monkeypatch):
     t = lambda a: torch.from_numpy(a).cuda()
     with pytest.raises(Exception):
         K.solve_with_symbol(t(np.asarray(Ai, np.int32)), t(np.asarray(Aj, np.int32)), t(Ax), t(b), sym)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cplx", [False, True])
+def test_row_blocked_multi_rhs_solve_vs_oracle(K, oracle, monkeypatch, cplx):
+    """lv_solve_grouped (plan.hpp: GroupProgram): many right-hand sides per system, rows of a
+    supernode blocked in registers; solve and transpose solve against the oracle and against the plain
+    level kernel."""
+    import torch
+    from klujax_b200 import synth
+    monkeypatch.setenv("KLUJAX_CUDA_FORCE_REGIME", "1")
+    g, L, r = 36, 8, 256
+    Ai, Aj, Ax = synth.poisson2d(g, L)
+    n = g * g
+    rng = np.random.default_rng(3)
+    Ax = Ax * (1.0 + 0.05 * rng.standard_normal(Ax.shape))
+    if cplx:
+        Ax = Ax * np.exp(1j * 0.2 * rng.standard_normal((L, 1)))
+    b = rng.standard_normal((L, n, r)) + (1j * rng.standard_normal((L, n, r)) if cplx else 0)
+    b = b.astype(Ax.dtype)
+    so = oracle.analyze(Ai, Aj, n)
+    ns = 2                                   # the oracle on two systems is enough (seconds)
+    ref = oracle.solve_with_symbol(Ai, Aj, Ax[:ns], b[:ns], so)
+    tref = oracle.solve_with_symbol(Ai, Aj, Ax[:ns], b[:ns], so, transpose=True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    tAi, tAj, tAx, tb = t(np.asarray(Ai, np.int32)), t(np.asarray(Aj, np.int32)), t(Ax), t(b)
+    out = {}
+    for grouped in ("1", "0"):
+        monkeypatch.setenv("KLUJAX_CUDA_GROUPED", grouped)
+        sym = K.analyze(Ai, Aj, n)
+        num = K.factor(tAi, tAj, tAx, sym)
+        x = K.solve_with_numeric(num, tb, sym).cpu().numpy()
+        xt = K.tsolve_with_numeric(num, tb, sym).cpu().numpy()
+        xs = K.solve_with_symbol(tAi, tAj, tAx, tb, sym).cpu().numpy()
+        assert _relerr(x[:ns], ref) < X_TOL and _relerr(xt[:ns], tref) < X_TOL and _relerr(xs[:ns], ref) < X_TOL, grouped
+        out[grouped] = (x, xt)
+        K.free_numeric(num)
+    assert _relerr(out["1"][0], out["0"][0]) < X_TOL and _relerr(out["1"][1], out["0"][1]) < X_TOL

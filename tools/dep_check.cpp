@@ -181,6 +181,71 @@ int main(int argc, char** argv) {
                     tr, pp.npanels, pp.ntemps, pp.maxE, pp.maxI, ext_lines, in_lines, steps, err);
         if (!(err < 1e-9)) rc = 1;  // a wrong program is off by O(1); badly scaled test matrices reach 1e-11
     }
+
+    // group programs (plan.hpp: GroupProgram), interpreted level by level the way lv_solve_grouped does;
+    // external reads once from a snapshot taken at the start of the level (what a concurrent group sees
+    // if it runs first) and once in place in sorted order (if it runs last): both must give x
+    for (int tr = 0; tr < 2; ++tr)
+        for (int snap = 0; snap < 2; ++snap) {
+            GroupProgram gp;
+            if (!build_group_program(ord, piv, lay, tr != 0, nullptr, gp)) {
+                std::printf("group program not built\n");
+                return 1;
+            }
+            std::vector<cd> X(n), S;
+            for (int k = 0; k < n; ++k) {
+                const int src = tr ? ord.Q[k] : piv.Pnum[k];
+                X[k] = tr ? b[src] : b[src] / Rs[src];
+            }
+            for (int l = 0; l < gp.nlevels; ++l) {
+                if (snap) S = X;
+                const std::vector<cd>& R = snap ? S : X;
+                for (int g = gp.level_ptr[l]; g < gp.level_ptr[l + 1]; ++g) {
+                    const int nk = gp.ghdr[4 * g], ko = gp.ghdr[4 * g + 1], nt = gp.ghdr[4 * g + 2] & 255, mb = (gp.ghdr[4 * g + 2] >> 8) & 255;
+                    const bool partial = (gp.ghdr[4 * g + 2] >> 30) & 1;
+                    const int* aux = &gp.gaux[(size_t)kGroupAux * gp.ghdr[4 * g + 3]];
+                    cd acc[kGroupRows];
+                    for (int i = 0; i < nt; ++i) acc[i] = R[aux[i]];
+                    for (int k = 0; k < nk; ++k) {
+                        const int* kr = &gp.krec[12 * ((size_t)ko + k)];
+                        const cd xv = R[kr[0]];
+                        for (int i = 0; i < nt; ++i)
+                            if (kr[1 + i] >= 0) acc[i] -= V[kr[1 + i]] * xv;
+                    }
+                    for (int i = 0; i < nt; ++i) {
+                        if (partial) {
+                            X[aux[i]] = acc[i];
+                            continue;
+                        }
+                        const cd val = ((mb >> i) & 1) ? acc[i] * V[aux[8 + i]] : acc[i];
+                        X[aux[i]] = val;
+                        for (int j = i + 1; j < nt; ++j) {
+                            const int sl = aux[16 + j * (j - 1) / 2 + i];
+                            if (sl >= 0) acc[j] -= V[sl] * val;
+                        }
+                    }
+                }
+            }
+            std::vector<cd> x(n);
+            for (int k = 0; k < n; ++k) {
+                const int dst = tr ? piv.Pnum[k] : ord.Q[k];
+                x[dst] = tr ? X[k] / Rs[dst] : X[k];
+            }
+            std::vector<cd> res(b);
+            std::vector<double> scale(n, 0.0);
+            for (int i = 0; i < n; ++i) scale[i] = std::abs(b[i]);
+            for (int e = 0; e < nz; ++e) {
+                if (!tr) res[Ai[e]] -= Ax[e] * x[Aj[e]], scale[Ai[e]] += std::abs(Ax[e]) * std::abs(x[Aj[e]]);
+                else res[Aj[e]] -= Ax[e] * x[Ai[e]], scale[Aj[e]] += std::abs(Ax[e]) * std::abs(x[Ai[e]]);
+            }
+            double err = 0;
+            for (int i = 0; i < n; ++i) err = std::max(err, std::abs(res[i]) / scale[i]);
+            if (snap == 0)
+                std::printf("group program (transpose %d): %d groups, %d levels, %lld multiply-adds in %lld k-steps (%.2f rows per read of X)\n", tr,
+                            gp.ngroups, gp.nlevels, (long long)gp.n_mac, (long long)gp.n_ksteps, (double)gp.n_mac / std::max<long long>(1, gp.n_ksteps));
+            std::printf("  %s: backward error %.3e\n", snap ? "level snapshot" : "in place", err);
+            if (!(err < 1e-9)) rc = 1;
+        }
     std::printf(rc ? "FAILED\n" : "OK\n");
     return rc;
 }
