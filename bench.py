@@ -378,7 +378,7 @@ def measure(K, name: str, lhs, steps: int, warmup: int, rank: int, world: int, d
         def step():
             _cabi.check(f_so(symh, L, _cabi.u64p(nh), L, n, r, P(b_d), P(x_d), sp))
         launches_per_step = 3
-        kernel = "lv_solve"
+        kernel = "lv_solve_grouped (row-blocked multi-right-hand-side solve)"
 
     flush = None
     if w.name == "cfg2":  # working set fits in the 126 MB L2: evict it between timed steps
