@@ -704,19 +704,19 @@ __global__ void __launch_bounds__(C * sizeof(typename Sc<T>::V) >= 32 ? 320 : 64
         for (int l = 0; l < a.nlevels; ++l) {
             const int tb = te;
             te = __ldg(a.level_ptr + l + 1);
-            if (ok)
+            if (ok) {
+                // header + row names of a task are three 16-byte words; those of the warp's NEXT task of
+                // the level are fetched while the current one runs
+                int4 hn0 = make_int4(0, 0, 0, 0), hn1 = hn0, hn2 = hn0;
+                if (tb + w < te) hn0 = __ldg(a.ghdr + 3 * (tb + w)), hn1 = __ldg(a.ghdr + 3 * (tb + w) + 1), hn2 = __ldg(a.ghdr + 3 * (tb + w) + 2);
                 for (int t = tb + w; t < te; t += NW) {
-                    const int4 h = __ldg(a.ghdr + t);
+                    const int4 h = hn0, q1 = hn1, q2 = hn2;
+                    if (t + NW < te) hn0 = __ldg(a.ghdr + 3 * (t + NW)), hn1 = __ldg(a.ghdr + 3 * (t + NW) + 1), hn2 = __ldg(a.ghdr + 3 * (t + NW) + 2);
                     const int nk = h.x, nt = h.z & 255, mulbits = (h.z >> 8) & 255;
                     const bool partial = (h.z >> 30) & 1;
                     const int4* kr = a.krec + 3 * static_cast<long long>(h.y);
                     const int* aux = a.gaux + static_cast<long long>(kGroupAux) * h.w;
-                    int rows[kGroupRows];
-#pragma unroll
-                    for (int i = 0; i < kGroupRows; i += 4) {
-                        const int4 q = __ldg(reinterpret_cast<const int4*>(aux + i));
-                        rows[i] = q.x, rows[i + 1] = q.y, rows[i + 2] = q.z, rows[i + 3] = q.w;
-                    }
+                    const int rows[kGroupRows] = {q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
                     V_t acc[kGroupRows][C];
 #pragma unroll
                     for (int i = 0; i < kGroupRows; ++i) {
@@ -806,6 +806,7 @@ __global__ void __launch_bounds__(C * sizeof(typename Sc<T>::V) >= 32 ? 320 : 64
                         }
                     }
                 }
+            }
             __syncthreads();
         }
         if (a.scale_out && ok) {

@@ -1278,13 +1278,14 @@ bool build_group_program(const Ordering& ord, const PivotPlan& piv, const SlotLa
     out.level_ptr.assign(out.nlevels + 1, 0);
     for (const Entry& e : entries) out.level_ptr[e.level]++;
     for (int l = 0; l < out.nlevels; ++l) out.level_ptr[l + 1] += out.level_ptr[l];
-    out.ghdr.reserve(4 * entries.size());
+    out.ghdr.reserve(12 * entries.size());
     for (int g : order) {
         const Entry& e = entries[g];
         out.ghdr.push_back(e.nk);
         out.ghdr.push_back(e.koff);
         out.ghdr.push_back(e.z);
         out.ghdr.push_back(e.aux);
+        for (int i = 0; i < kGroupRows; ++i) out.ghdr.push_back(out.gaux[static_cast<size_t>(kGroupAux) * e.aux + i]);  // row names
     }
     if (out.krec.empty()) out.krec.assign(12, -1);
     return out.ngroups > 0;

@@ -197,8 +197,9 @@ bool build_panel_program(const Ordering& ord, const PivotPlan& piv, const SlotLa
 // entry there; dependencies between rows of one group are resolved thread-locally (every thread
 // has all rows of its own columns).  Groups are levelled like tasks (fewer, wider levels: a chain of
 // rows inside a supernode collapses into its groups).
-//   ghdr  4 ints per task (sorted by level): k-steps, first k-step, rows | multiply bits << 8 (bit 30: a PARTIAL
-//         task - X[rows] -= sum over its chunk of k-steps, nothing else), index of aux
+//   ghdr  12 ints per task (sorted by level): k-steps, first k-step, rows | multiply bits << 8 (bit 30: a PARTIAL
+//         task - X[rows] -= sum over its chunk of k-steps, nothing else), index of aux, row names [8] (one load
+//         of three 16-byte words, prefetched for the warp's next task)
 //   gaux  kGroupAux ints per group: row names [8], pivot slots [8] (-1 none), in-group slots [28]
 //         (row j <- row i at j*(j-1)/2 + i, -1 none; -2: row j continues row i, coefficient -1)
 //   krec  12 ints per k-step: row name of the operand, value slot per row of the group [8] (-1 none), mask of

@@ -201,9 +201,11 @@ int main(int argc, char** argv) {
                 if (snap) S = X;
                 const std::vector<cd>& R = snap ? S : X;
                 for (int g = gp.level_ptr[l]; g < gp.level_ptr[l + 1]; ++g) {
-                    const int nk = gp.ghdr[4 * g], ko = gp.ghdr[4 * g + 1], nt = gp.ghdr[4 * g + 2] & 255, mb = (gp.ghdr[4 * g + 2] >> 8) & 255;
-                    const bool partial = (gp.ghdr[4 * g + 2] >> 30) & 1;
-                    const int* aux = &gp.gaux[(size_t)kGroupAux * gp.ghdr[4 * g + 3]];
+                    const int nk = gp.ghdr[12 * g], ko = gp.ghdr[12 * g + 1], nt = gp.ghdr[12 * g + 2] & 255, mb = (gp.ghdr[12 * g + 2] >> 8) & 255;
+                    const bool partial = (gp.ghdr[12 * g + 2] >> 30) & 1;
+                    const int* aux = &gp.gaux[(size_t)kGroupAux * gp.ghdr[12 * g + 3]];
+                    for (int i = 0; i < nt; ++i)
+                        if (gp.ghdr[12 * g + 4 + i] != aux[i]) return 4;
                     cd acc[kGroupRows];
                     for (int i = 0; i < nt; ++i) acc[i] = R[aux[i]];
                     for (int k = 0; k < nk; ++k) {
