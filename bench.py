@@ -196,8 +196,12 @@ def bind_to_gpu_numa(local_rank: int) -> str:
         dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
         path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
         node = int(open(path).read().strip())
-        if node < 0:
-            return "numa node unknown"
+        if node < 0:  # virtualised PCI topology: say what the box offers instead of guessing
+            try:
+                online = open("/sys/devices/system/node/online").read().strip()
+            except OSError:
+                online = "?"
+            return f"GPU's numa node not exposed (nodes online: {online}; {len(os.sched_getaffinity(0))} cpus allowed): nothing to bind"
         cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
         ids = set()
         for part in cpus.split(","):
