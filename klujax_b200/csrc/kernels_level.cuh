@@ -631,7 +631,7 @@ constexpr int kGroupKC = 16;  // k-steps staged per chunk
 template <typename V_t, int C>
 constexpr size_t grouped_warp_bytes() {
     return (static_cast<size_t>(kGroupKC) * 32 * C + static_cast<size_t>(kGroupKC) * kGroupRows + 36) * sizeof(V_t) +
-           static_cast<size_t>(kGroupKC) * 12 * sizeof(int);
+           (static_cast<size_t>(kGroupKC) * 12 + 16) * sizeof(int);
 }
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
@@ -674,6 +674,7 @@ __global__ void __launch_bounds__(C * sizeof(typename Sc<T>::V) >= 32 ? 320 : 64
     V_t* scf = sx + KC * 32 * C;                                                      // [KC][8]
     V_t* sin = scf + KC * kGroupRows;                                                 // [36]: pivots [8], in-group entries [28]
     int* srec = reinterpret_cast<int*>(sin + 36);                                     // [KC][12]
+    int* srow = srec + KC * 12;                                                       // [8]: row names of the task (keeps them out of registers)
     const int cols_per_cta = 32 * C;
     const long long slices_per_sys = (a.r + cols_per_cta - 1) / cols_per_cta;
     const long long nslices = static_cast<long long>(a.Q / a.r) * slices_per_sys;
@@ -704,7 +705,8 @@ __global__ void __launch_bounds__(C * sizeof(typename Sc<T>::V) >= 32 ? 320 : 64
         for (int l = 0; l < a.nlevels; ++l) {
             const int tb = te;
             te = __ldg(a.level_ptr + l + 1);
-            if (ok) {
+            {   // ALL lanes walk the tasks (the staging uses warp-wide synchronisation): lanes beyond the last
+                // column of the system compute on column 0 and never store
                 // header + row names of a task are three 16-byte words; those of the warp's NEXT task of
                 // the level are fetched while the current one runs
                 int4 hn0 = make_int4(0, 0, 0, 0), hn1 = hn0, hn2 = hn0;
@@ -717,6 +719,11 @@ __global__ void __launch_bounds__(C * sizeof(typename Sc<T>::V) >= 32 ? 320 : 64
                     const int4* kr = a.krec + 3 * static_cast<long long>(h.y);
                     const int* aux = a.gaux + static_cast<long long>(kGroupAux) * h.w;
                     const int rows[kGroupRows] = {q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+                    __syncwarp();
+                    if (lane == 0) {
+                        *reinterpret_cast<int4*>(srow) = q1;
+                        *reinterpret_cast<int4*>(srow + 4) = q2;
+                    }
                     V_t acc[kGroupRows][C];
 #pragma unroll
                     for (int i = 0; i < kGroupRows; ++i) {
@@ -782,7 +789,7 @@ __global__ void __launch_bounds__(C * sizeof(typename Sc<T>::V) >= 32 ? 320 : 64
                     if (partial) {  // a chunk of the group's k-steps applied early: X[rows] -= sum, in place
 #pragma unroll
                         for (int i = 0; i < kGroupRows; ++i)
-                            if (i < nt) st_cols<V_t, C>(xp(rows[i]), acc[i]);
+                            if (i < nt && ok) st_cols<V_t, C>(xp(srow[i]), acc[i]);
                         continue;
                     }
                     // rows of the group, in order: finish, store, feed the later rows of the group
@@ -794,7 +801,7 @@ __global__ void __launch_bounds__(C * sizeof(typename Sc<T>::V) >= 32 ? 320 : 64
 #pragma unroll
                                 for (int j = 0; j < C; ++j) acc[i][j] = S::mul(acc[i][j], dv);
                             }
-                            st_cols<V_t, C>(xp(rows[i]), acc[i]);
+                            if (ok) st_cols<V_t, C>(xp(srow[i]), acc[i]);
 #pragma unroll
                             for (int jr = i + 1; jr < kGroupRows; ++jr) {
                                 if (jr < nt) {
