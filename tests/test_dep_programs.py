@@ -170,3 +170,65 @@ def test_row_blocked_multi_rhs_solve_vs_oracle(K, oracle, monkeypatch, cplx, g, 
         out[grouped] = (x, xt)
         K.free_numeric(num)
     assert _relerr(out["1"][0], out["0"][0]) < X_TOL and _relerr(out["1"][1], out["0"][1]) < X_TOL
+
+
+@pytest.mark.gpu
+def test_row_blocked_solve_on_fuzzed_structures(K, monkeypatch):
+    """lv_solve_grouped and panel_solve over structures with hidden diagonals, arrow heads, BTF chains with
+    off-diagonal blocks, dense blocks and bands (seeded), 32 right-hand sides per system: x and the
+    transpose solve against dense LAPACK."""
+    import torch
+    monkeypatch.setenv("KLUJAX_CUDA_FORCE_REGIME", "1")
+    rng = np.random.default_rng(4321)
+
+    def pattern(kind, n):
+        A = np.zeros((n, n))
+        if kind == "random":
+            A = rng.standard_normal((n, n)) * (rng.random((n, n)) < min(0.5, 4.0 / n))
+        elif kind == "arrow":
+            A[0, :] = rng.standard_normal(n); A[:, 0] = rng.standard_normal(n); A[-1, :] = rng.standard_normal(n)
+        elif kind == "btf":
+            k = 0
+            while k < n:
+                m = int(rng.integers(1, 9)); e = min(n, k + m)
+                A[k:e, k:e] = rng.standard_normal((e - k, e - k))
+                if e < n:
+                    A[k:e, e:] = rng.standard_normal((e - k, n - e)) * (rng.random((e - k, n - e)) < 0.1)
+                k = e
+        elif kind == "dense":
+            A = rng.standard_normal((n, n))
+        elif kind == "band":
+            for d in range(-3, 4):
+                A += np.diag(rng.standard_normal(n - abs(d)), d)
+        A[np.arange(n), np.arange(n)] = 0.0
+        A += np.diag(2.0 + np.abs(A).sum(1))
+        return A[rng.permutation(n)]
+
+    for kind, n, cplx in (("random", 90, False), ("arrow", 48, True), ("btf", 130, False), ("dense", 40, True), ("band", 120, False)):
+        A = pattern(kind, n)
+        Ai, Aj = (v.astype(np.int32) for v in np.nonzero(A))
+        for L, r in ((64, 32), (3, 2)):   # row-blocked solve / panel solve
+            Ax = np.tile(A[Ai, Aj], (L, 1)) * (1.0 + 1e-4 * rng.standard_normal((L, Ai.size)))  # same pivots for every system
+            b = rng.standard_normal((L, n, r))
+            if cplx:
+                Ax = Ax * (1.0 + 0.1j)
+                b = b + 1j * rng.standard_normal((L, n, r))
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+            res = {}
+            for new_kernels in ("1", "0"):  # default kernels, then the plain level kernels on the same factors
+                monkeypatch.setenv("KLUJAX_CUDA_DEP", new_kernels)
+                monkeypatch.setenv("KLUJAX_CUDA_GROUPED", new_kernels)
+                sym = K.analyze(Ai, Aj, n)
+                num = K.factor(t(Ai), t(Aj), t(Ax), sym)
+                res[new_kernels] = (K.solve_with_numeric(num, t(b), sym).cpu().numpy(),
+                                    K.tsolve_with_numeric(num, t(b), sym).cpu().numpy())
+                K.free_numeric(num)
+            x, xt = res["1"]
+            assert _relerr(x, res["0"][0]) < 1e-9 and _relerr(xt, res["0"][1]) < 1e-9, (kind, n, L, r)
+            # the transversal need not recover the dominant diagonal of a row-permuted matrix, so KLU's
+            # tol = 1e-3 pivoting may run on small pivots: a loose bar against dense LAPACK
+            for m in range(0, L, max(1, L // 4)):
+                D = np.zeros((n, n), dtype=Ax.dtype)
+                D[Ai, Aj] = Ax[m]
+                assert _relerr(x[m], np.linalg.solve(D, b[m])) < 1e-6, (kind, n, L, r, m)
+                assert _relerr(xt[m], np.linalg.solve(D.T, b[m])) < 1e-6, (kind, n, L, r, m)
