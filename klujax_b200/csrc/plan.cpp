@@ -931,7 +931,8 @@ bool build_panel_program(const Ordering& ord, const PivotPlan& piv, const SlotLa
             pt.div = -1;
             pt.mul = false;
             pt.noinit = true;
-            pt.ops.assign(ops.begin() + done, ops.begin() + done + kPanelChunk);
+            pt.ops.reserve(kPanelChunk);
+            for (int q = 0; q < kPanelChunk; ++q) pt.ops.push_back(ops[done + q]);
             done += kPanelChunk;
             temps.push_back(n + temp_next);
             temp_next = (temp_next + 1) % ring;
@@ -943,7 +944,7 @@ bool build_panel_program(const Ordering& ord, const PivotPlan& piv, const SlotLa
         t.div = div;
         t.mul = mul;
         t.noinit = false;
-        t.ops.assign(ops.begin() + done, ops.end());
+        for (size_t q = done; q < ops.size(); ++q) t.ops.push_back(ops[q]);
         for (int tr : temps) t.ops.push_back({-2, tr, 0});  // acc -= (-1) * partial
         out.n_mac += static_cast<int64_t>(ops.size());
         last_writer[row] = static_cast<int>(seq.size());
