@@ -50,7 +50,7 @@ struct DepColProg {
     int4* d_colinfo = nullptr;
     int* d_ccand = nullptr;
     int4* d_urec = nullptr;
-    uint16_t* d_dest = nullptr;
+    int* d_dest = nullptr;
     ~DepColProg() {
         if (d_colinfo) cudaFree(d_colinfo);
         if (d_ccand) cudaFree(d_ccand);
@@ -69,7 +69,7 @@ struct DepColProg {
         return up(reinterpret_cast<void**>(&d_colinfo), cp.colinfo.data(), cp.colinfo.size() * sizeof(int)) &&
                up(reinterpret_cast<void**>(&d_ccand), cp.ccand.data(), cp.ccand.size() * sizeof(int)) &&
                up(reinterpret_cast<void**>(&d_urec), cp.urec.data(), cp.urec.size() * sizeof(int)) &&
-               up(reinterpret_cast<void**>(&d_dest), cp.dest.data(), cp.dest.size() * sizeof(uint16_t));
+               up(reinterpret_cast<void**>(&d_dest), cp.dest.data(), cp.dest.size() * sizeof(int));
     }
 };
 
@@ -107,8 +107,9 @@ struct DepArgs {
     const int4* colinfo;
     const int* ccand;
     const int4* urec;
-    const uint16_t* dest;
+    const int* dest;
     int scratch_elems;  // values per warp buffer; longer columns are updated in place in global memory
+    int stage_elems;    // staged entries of L (and destinations) per warp and chunk of records
     // solves
     const int4 *hdr, *lane;
     const int *ext_slot, *ext_idx, *in_slot;
@@ -132,23 +133,39 @@ struct DepArgs {
     unsigned long long* prof;  // KLUJAX_CUDA_DEP_PROF=1: cycle counters per phase (summed over warps)
 };
 
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+
 // A waiting warp must not spin: 32 warps polling shared memory take the issue slots and the
 // shared-memory pipe from the one warp everybody is waiting for (measured on cfg 4: the solve ran
 // 2x SLOWER than the level kernel with plain spinning).  __nanosleep takes the warp off the
 // scheduler between two polls.
 __device__ __forceinline__ void dep_wait_flag(const volatile unsigned char* f, unsigned ns) {
-    while (*f == 0) __nanosleep(ns);
+    // back-off: the warp the chain is waiting for has waited briefly, the ones far ahead of the frontier poll rarely
+    const unsigned cap = 8 * ns + 32;
+    while (*f == 0) {
+        __nanosleep(ns);
+        ns = min(2 * ns + 8, cap);
+    }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(1024, 1) dep_factor(const DepArgs a) {
+__global__ void __launch_bounds__(512, 1) dep_factor(const DepArgs a) {
     using S = Sc<T>;
     using V_t = typename S::V;
     extern __shared__ __align__(16) unsigned char dep_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int fl_bytes = (a.n + 15) & ~15;
     volatile unsigned char* flags = dep_smem;
-    V_t* scratch = reinterpret_cast<V_t*>(dep_smem + fl_bytes) + static_cast<size_t>(w) * a.scratch_elems;
+    // per warp: column buffer [scratch_elems], staged entries of L [stage_elems], their destinations [stage_elems]
+    const size_t warp_bytes = (static_cast<size_t>(a.scratch_elems) + a.stage_elems) * sizeof(V_t) + static_cast<size_t>(a.stage_elems) * sizeof(int);
+    unsigned char* wb = dep_smem + fl_bytes + static_cast<size_t>(w) * warp_bytes;
+    V_t* scratch = reinterpret_cast<V_t*>(wb);
+    V_t* st_l = scratch + a.scratch_elems;
+    int* st_d = reinterpret_cast<int*>(st_l + a.stage_elems);
     const long long ls = a.lpad;
     for (int m = blockIdx.x; m < a.L; m += gridDim.x) {
         for (int i = threadIdx.x; i < fl_bytes / 4; i += blockDim.x) reinterpret_cast<volatile unsigned*>(dep_smem)[i] = 0u;
@@ -176,48 +193,59 @@ __global__ void __launch_bounds__(1024, 1) dep_factor(const DepArgs a) {
                 for (int p = lane; p < nc; p += 32) scratch[p] = Vc[static_cast<long long>(p) * ls];
             __syncwarp();
             DEP_TICK(0)  // column info + column load
-            // Update records in batches of UB: the records, the destination positions and - for the
-            // columns j that are already final - the entries of L(:,j) of the whole batch are in flight
-            // together (one memory round trip per batch, not per record; a dense-ish column has
-            // hundreds of records).  A lane covers entries lane, lane + 32, ... of L(:,j); the first
-            // one of every record is prefetched, the rest (rare: |L(:,j)| > 32) is loaded in the loop.
-            constexpr int UB = 4;
-            for (int u0 = 0; u0 < nu; u0 += UB) {
-                int4 rc[UB];
-                int d0[UB];
-                V_t l0[UB];
-                bool have[UB];
+            // Update records in chunks of up to 32: lane r holds record u0 + r.  For the columns j that are
+            // final already, the entries of L(:,j) and their destination positions of the WHOLE chunk are
+            // brought into the warp's staging area with cp.async (one memory round trip per chunk; a
+            // dense-ish column has hundreds of records), then the records are applied in order out of
+            // shared memory.  A record whose column is not final yet is waited for when its turn comes.
+            for (int u0 = 0; u0 < nu;) {
+                const int ntry = min(32, nu - u0);
+                int4 rc = make_int4(0, 0, 0, 0);
+                if (lane < ntry) rc = __ldg(a.urec + ci.w + u0 + lane);
+                const bool ready = lane < ntry && flags[rc.x] != 0;
+                int cnt = lane < ntry ? min(rc.z, 32) : 0;  // staged entries of my record (destinations always, entries of L if final)
+                int off = cnt;
 #pragma unroll
-                for (int i = 0; i < UB; ++i)
-                    rc[i] = u0 + i < nu ? __ldg(a.urec + ci.w + u0 + i) : make_int4(0, 0, 0, 0);
-#pragma unroll
-                for (int i = 0; i < UB; ++i) {
-                    d0[i] = lane < rc[i].z ? static_cast<int>(__ldg(a.dest + rc[i].w + lane)) : 0;
-                    have[i] = u0 + i < nu && flags[rc[i].x] != 0;  // warp-uniform
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, off, o);
+                    if (lane >= o) off += v;
                 }
+                off -= cnt;
+                const unsigned fits = __ballot_sync(0xffffffffu, off + cnt <= a.stage_elems);
+                const unsigned rdy = __ballot_sync(0xffffffffu, ready);
+                const int nrec = min(ntry, (~fits) ? __ffs(~fits) - 1 : 32);
                 __threadfence_block();
-                DEP_TICK(1)  // records + destinations + flags of the batch
-#pragma unroll
-                for (int i = 0; i < UB; ++i)
-                    if (have[i] && lane < rc[i].z) l0[i] = Vs[static_cast<long long>(rc[i].y + lane) * ls];
-#pragma unroll
-                for (int i = 0; i < UB; ++i) {
-                    if (u0 + i >= nu) break;
-                    const int lbeg = rc[i].y, lcnt = rc[i].z;
-                    if (!have[i]) {
-                        dep_wait_flag(flags + rc[i].x, a.sleep_ns);
+                DEP_TICK(1)  // records + flags of the chunk
+                for (int r = 0; r < nrec; ++r) {
+                    const int lc = __shfl_sync(0xffffffffu, cnt, r), lb = __shfl_sync(0xffffffffu, rc.y, r),
+                              dp = __shfl_sync(0xffffffffu, rc.w, r), of = __shfl_sync(0xffffffffu, off, r);
+                    if (lane < lc) {
+                        if ((rdy >> r) & 1u) cp_async<sizeof(V_t)>(st_l + of + lane, Vs + static_cast<long long>(lb + lane) * ls);
+                        cp_async<4>(st_d + of + lane, a.dest + dp + lane);
+                    }
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
+                for (int r = 0; r < nrec; ++r) {
+                    const int j = __shfl_sync(0xffffffffu, rc.x, r), lbeg = __shfl_sync(0xffffffffu, rc.y, r),
+                              lcnt = __shfl_sync(0xffffffffu, rc.z, r), dp = __shfl_sync(0xffffffffu, rc.w, r),
+                              of = __shfl_sync(0xffffffffu, off, r);
+                    const bool staged = (rdy >> r) & 1u;
+                    if (!staged) {
+                        dep_wait_flag(flags + j, a.sleep_ns);
                         __threadfence_block();
                         DEP_TICK(2)  // waiting for a column
-                        if (lane < lcnt) l0[i] = Vs[static_cast<long long>(lbeg + lane) * ls];
                     }
-                    const V_t uv = cget(u0 + i);
+                    const V_t uv = cget(u0 + r);
                     if (lane < lcnt) {
-                        V_t t = cget(d0[i]);
-                        S::fms_acc(t, l0[i], uv);
-                        cset(d0[i], t);
+                        const int d = st_d[of + lane];
+                        const V_t l = staged ? st_l[of + lane] : Vs[static_cast<long long>(lbeg + lane) * ls];
+                        V_t t = cget(d);
+                        S::fms_acc(t, l, uv);
+                        cset(d, t);
                     }
-                    for (int q = lane + 32; q < lcnt; q += 32) {
-                        const int d = static_cast<int>(__ldg(a.dest + rc[i].w + q));
+                    for (int q = lane + 32; q < lcnt; q += 32) {  // rare: more than 32 entries in L(:,j)
+                        const int d = __ldg(a.dest + dp + q);
                         const V_t l = Vs[static_cast<long long>(lbeg + q) * ls];
                         V_t t = cget(d);
                         S::fms_acc(t, l, uv);
@@ -225,7 +253,8 @@ __global__ void __launch_bounds__(1024, 1) dep_factor(const DepArgs a) {
                     }
                     __syncwarp();
                 }
-                DEP_TICK(3)  // applying the batch (includes the latency of the prefetched L entries)
+                DEP_TICK(3)  // applying the chunk
+                u0 += nrec;
             }
             const V_t pv = cget(nu);
             bad |= S::bad_pivot(pv);
@@ -404,6 +433,11 @@ __global__ void __launch_bounds__(32 * kPanelWarps, 1) panel_solve(const DepArgs
 // ---- host side -------------------------------------------------------------------------------
 constexpr size_t kDepSmemMax = 227 * 1024;
 
+static int dep_env_int_early(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
 static bool dep_enabled() {
     if (const char* e = std::getenv("KLUJAX_CUDA_DEP")) return std::atoi(e) != 0;
     return true;
@@ -411,22 +445,22 @@ static bool dep_enabled() {
 
 struct DepFactorPlan {
     bool ok = false;
-    int scratch_elems = 0;
+    int scratch_elems = 0, stage_elems = 0, warps = 0;
     size_t smem = 0;
 };
 static DepFactorPlan dep_factor_plan(int n, int maxcol, size_t vsz) {
     DepFactorPlan p;
     const size_t fl = (static_cast<size_t>(n) + 15) & ~size_t(15);
-    // the warp buffers + flags take at most ~160 KB: the rest of the SM's 256 KB stays L1 for L(:,j)
-    size_t budget = 160 * 1024;
-    if (const char* e = std::getenv("KLUJAX_CUDA_DEP_SMEM_KB")) budget = static_cast<size_t>(std::atoi(e)) * 1024;
-    budget = std::min(budget, kDepSmemMax);
-    if (fl + 32 * 64 * vsz > budget) return p;
-    size_t se = (budget - fl) / (32 * vsz);
+    p.warps = std::min(16, std::max(1, dep_env_int_early("KLUJAX_CUDA_DEP_FACTOR_WARPS", 16)));
+    p.stage_elems = 512;
+    size_t budget = 200 * 1024;
+    if (fl + static_cast<size_t>(p.warps) * (64 * vsz + p.stage_elems * (vsz + 4)) > budget) return p;
+    size_t se = (budget - fl) / p.warps;
+    se = (se - p.stage_elems * (vsz + 4)) / vsz;
     se = std::min<size_t>(se, static_cast<size_t>((maxcol + 1) & ~1));
     se &= ~size_t(1);
     p.scratch_elems = static_cast<int>(se);
-    p.smem = fl + 32 * se * vsz;
+    p.smem = fl + static_cast<size_t>(p.warps) * ((se + p.stage_elems) * vsz + p.stage_elems * 4);
     p.ok = true;
     return p;
 }

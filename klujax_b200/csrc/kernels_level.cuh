@@ -633,12 +633,6 @@ constexpr size_t grouped_warp_bytes() {
     return (static_cast<size_t>(kGroupKC) * 32 * C + static_cast<size_t>(kGroupKC) * kGroupRows + 36) * sizeof(V_t) +
            (static_cast<size_t>(kGroupKC) * 12 + 16) * sizeof(int);
 }
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
-    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
-}
-
 struct GrpArgs {
     const int4* ghdr;
     const int4* krec;   // 3 per k-step
@@ -1084,9 +1078,10 @@ static int level_run_t(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::st
             DepArgs d = {};
             d.colinfo = c.dep_col->d_colinfo; d.ccand = c.dep_col->d_ccand; d.urec = c.dep_col->d_urec; d.dest = c.dep_col->d_dest;
             d.scratch_elems = fp.scratch_elems;
+            d.stage_elems = fp.stage_elems;
             d.n = c.n; d.L = c.L; d.V = V; d.lpad = v_slot; d.vss = v_sys; d.sysidx = c.sysidx; d.bad = bad; d.growth2 = growth2;
-            if (!chk(dep_launch(dep_factor<T>, static_cast<int>(std::min<long long>(c.L, 2LL * c.num_sms)),
-                                32 * std::min(32, std::max(1, dep_env_int("KLUJAX_CUDA_DEP_FACTOR_WARPS", 32))), fp.smem, c.st, d, 100), "dependency-driven factor")) {
+            if (!chk(dep_launch(dep_factor<T>, static_cast<int>(std::min<long long>(c.L, 2LL * c.num_sms)), 32 * fp.warps, fp.smem, c.st, d, 40),
+                     "dependency-driven factor")) {
                 cleanup();
                 return KLU_OUT_OF_MEMORY;
             }

@@ -387,7 +387,7 @@ static DepColProg* get_dep_col(Symbolic* S, int cx) {
     Seeded& sd = S->seeded[cx];
     if (!sd.dep_col_tried) {
         sd.dep_col_tried = true;
-        int64_t cap = 64LL << 20;  // multiply-adds: the 16-bit destination list is 2 bytes each
+        int64_t cap = 64LL << 20;  // multiply-adds: the destination list is 4 bytes each
         if (const char* e = std::getenv("KLUJAX_CUDA_DEP_MAXMAC")) cap = std::atoll(e);
         if (sd.info_mac <= cap) {
             ColProgram cp;

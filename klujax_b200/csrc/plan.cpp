@@ -845,7 +845,6 @@ bool build_col_program(const PivotPlan& piv, const SlotLayout& lay, ColProgram& 
     for (int k = 0; k < n; ++k) {
         const int cb = lay.col_begin[k], dg = lay.diag_slot[k], ce = lay.col_begin[k + 1];
         const int nc = ce - cb;
-        if (nc > 65535) return false;  // positions inside a column are 16-bit
         out.maxcol = std::max(out.maxcol, nc);
         out.colinfo[4 * k + 0] = cb;
         out.colinfo[4 * k + 1] = dg - cb;
@@ -864,7 +863,7 @@ bool build_col_program(const PivotPlan& piv, const SlotLayout& lay, ColProgram& 
             for (int sl = lbeg; sl < lbeg + lcnt; ++sl) {
                 const int p = pos[lay.slot_row[sl]];
                 if (p < 0) return false;  // the pattern of column k always contains L(:,j) below row j
-                out.dest.push_back(static_cast<uint16_t>(p));
+                out.dest.push_back(p);
             }
             out.n_mac += lcnt;
             d = std::max(d, depth[j]);

@@ -158,7 +158,7 @@ struct ColProgram {
     std::vector<int> ccand;      // per column: -2 diagonal pivot, -1 off-diagonal pivot, else position (inside the
                                  // column) of the diagonal candidate that failed the threshold test (plan.hpp: TK_MUL_TRACK_*)
     std::vector<int> urec;       // 4 per U entry, in slot order: pivot column j, first slot of L(:,j), its length, offset into dest
-    std::vector<uint16_t> dest;  // per multiply-add: position of the destination inside column k
+    std::vector<int> dest;       // per multiply-add: position of the destination inside column k
     int64_t n_mac = 0;
 };
 bool build_col_program(const PivotPlan& piv, const SlotLayout& lay, ColProgram& out);
