@@ -21,6 +21,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "kernels_dep.cuh"
 #include "kernels_small.cuh"
 #include "plan.hpp"
@@ -1254,25 +1256,48 @@ static int level_run(const LevelCall& c, LevelProg* pf, LevelProg* ps, std::stri
 }
 
 // ---- dot_f64 / dot_c128: b[m,i,k] = sum_e Ax[m,e] * x[m,Aj[e],k] over Ai[e] = i ----
+// Deterministic: the entries are grouped by row with a STABLE radix sort of the call's (Ai, e) pairs
+// (cub), then a thread per (system, row, column) adds the products of its row in the order the
+// entries arrive in the COO list - the summation order of the reference's serial loop
+// (/root/reference/klujax.cpp:165-249) - and writes b once.  (Round 1 used a thread per product
+// with atomicAdd: non-deterministic rounding, uncoalesced.)
+__global__ void spmm_keys_kernel(int nz, int n, const int* __restrict__ Ai, const int* __restrict__ Aj,
+                                 int* __restrict__ key, int* __restrict__ val) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nz) return;
+    const int i = Ai[e], j = Aj[e];
+    key[e] = (i < 0 || i >= n || j < 0 || j >= n) ? n : i;  // entries out of range form a last bucket nobody reads
+    val[e] = e;
+}
+__global__ void spmm_rowptr_kernel(int nz, int n, const int* __restrict__ skey, int* __restrict__ rowptr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int lo = 0, hi = nz;  // first position whose key is >= i
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (skey[mid] < i) lo = mid + 1;
+        else hi = mid;
+    }
+    rowptr[i] = lo;
+}
 template <typename T>
-__global__ void spmm_kernel(int L, int n, int r, int nz, const int* __restrict__ Ai,
+__global__ void spmm_kernel(int L, int n, int r, int nz, const int* __restrict__ rowptr, const int* __restrict__ sval,
                             const int* __restrict__ Aj, const typename Sc<T>::V* __restrict__ Ax,
-                            const typename Sc<T>::V* __restrict__ x, double* __restrict__ b) {
+                            const typename Sc<T>::V* __restrict__ x, typename Sc<T>::V* __restrict__ b) {
+    using S = Sc<T>;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)L * nz * r;
+    const long long total = (long long)L * n * r;
     if (tid >= total) return;
     const int k = static_cast<int>(tid % r);
     const long long t2 = tid / r;
-    const int e = static_cast<int>(t2 % nz);
-    const long long m = t2 / nz;
-    const int i = Ai[e], j = Aj[e];
-    if (i < 0 || i >= n || j < 0 || j >= n) return;
-    const typename Sc<T>::V p = Sc<T>::mul(Ax[m * nz + e], x[(m * n + j) * r + k]);
-    constexpr int W = sizeof(typename Sc<T>::V) / sizeof(double);
-    double* dst = b + ((m * n + i) * r + k) * W;
-    const double* pv = reinterpret_cast<const double*>(&p);
-#pragma unroll
-    for (int w = 0; w < W; ++w) atomicAdd(dst + w, pv[w]);
+    const int i = static_cast<int>(t2 % n);
+    const long long m = t2 / n;
+    typename S::V acc = S::zero();
+    for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+        const int e = sval[p];
+        S::fma_acc(acc, Ax[m * nz + e], x[(m * n + Aj[e]) * r + k]);
+    }
+    b[tid] = acc;
 }
 
 // dAx[m][e] = sum_k ct[m][Ai[e]][k] * x[m][Aj[e]][k]: transpose of the product above with
@@ -1317,24 +1342,43 @@ static int coo_sddmm(int cx, int L, int n, int r, int nz, const int* Ai, const i
 
 static int coo_spmm(int cx, int L, int n, int r, int nz, const int* Ai, const int* Aj,
                     const double* Ax, const double* x, double* b, cudaStream_t st, std::string& err) {
-    const size_t bytes = sizeof(double) * (cx ? 2 : 1) * (size_t)L * n * r;
-    if (cudaMemsetAsync(b, 0, bytes, st) != cudaSuccess) {
-        err = "dot: memset failed";
-        return KLU_INVALID;
-    }
-    const long long total = (long long)L * nz * r;
+    const long long total = (long long)L * n * r;
     if (total == 0) return 0;
-    const unsigned grid = static_cast<unsigned>((total + 255) / 256);
-    if (cx)
-        spmm_kernel<zc><<<grid, 256, 0, st>>>(L, n, r, nz, Ai, Aj, reinterpret_cast<const double2*>(Ax),
-                                              reinterpret_cast<const double2*>(x), b);
-    else
-        spmm_kernel<double><<<grid, 256, 0, st>>>(L, n, r, nz, Ai, Aj, Ax, x, b);
-    if (cudaGetLastError() != cudaSuccess) {
-        err = "dot: launch failed";
+    auto bad = [&](const char* what) {
+        err = std::string("dot: ") + what;
+        cudaGetLastError();
         return KLU_INVALID;
+    };
+    // scratch (stream-ordered): keys / entry ids before and after the sort, row pointers, cub's own
+    int* scratch = nullptr;
+    const size_t nzp = static_cast<size_t>(std::max(nz, 1));
+    if (cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(int) * (4 * nzp + n + 2), st) != cudaSuccess) return bad("out of device memory");
+    int *key = scratch, *val = key + nzp, *skey = val + nzp, *sval = skey + nzp, *rowptr = sval + nzp;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int end_bit = 1;
+    while ((1 << end_bit) <= n && end_bit < 31) ++end_bit;  // keys are 0..n
+    int rc = 0;
+    if (nz > 0) {
+        spmm_keys_kernel<<<(nz + 255) / 256, 256, 0, st>>>(nz, n, Ai, Aj, key, val);
+        if (cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, skey, val, sval, nz, 0, end_bit, st) != cudaSuccess ||
+            cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 16), st) != cudaSuccess ||
+            cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, skey, val, sval, nz, 0, end_bit, st) != cudaSuccess)
+            rc = bad("sorting the entries by row failed");
     }
-    return 0;
+    if (!rc) {
+        spmm_rowptr_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(nz, n, skey, rowptr);
+        const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+        if (cx)
+            spmm_kernel<zc><<<grid, 256, 0, st>>>(L, n, r, nz, rowptr, sval, Aj, reinterpret_cast<const double2*>(Ax),
+                                                  reinterpret_cast<const double2*>(x), reinterpret_cast<double2*>(b));
+        else
+            spmm_kernel<double><<<grid, 256, 0, st>>>(L, n, r, nz, rowptr, sval, Aj, Ax, x, b);
+        if (cudaGetLastError() != cudaSuccess) rc = bad("launch failed");
+    }
+    if (tmp) cudaFreeAsync(tmp, st);
+    cudaFreeAsync(scratch, st);
+    return rc;
 }
 
 }  // namespace kb

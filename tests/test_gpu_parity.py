@@ -330,6 +330,30 @@ def test_dot_vs_dense(K, dtype):
         assert relerr(got[m], dense(Ai, Aj, Ax[m], 5) @ x[m]) < 1e-13
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dot_is_deterministic_and_sums_duplicates_in_coo_order(K, dtype):
+    """`dot` groups the entries by row with a stable sort and adds them in COO order (the order of the
+    reference's serial loop, klujax.cpp:165-249): repeated calls agree bit for bit, duplicated and
+    unsorted entries are summed, rows without entries come out as exact zeros."""
+    rng = np.random.default_rng(17)
+    n, nz, L, r = 300, 4000, 7, 3
+    Ai = rng.integers(0, n - 5, nz).astype(np.int32)   # the last five rows have no entries
+    Aj = rng.integers(0, n, nz).astype(np.int32)
+    Ax = rng.standard_normal((L, nz)).astype(dtype)
+    x = rng.standard_normal((L, n, r)).astype(dtype)
+    if np.issubdtype(np.dtype(dtype), np.complexfloating):
+        Ax = Ax + 1j * rng.standard_normal((L, nz))
+        x = x + 1j * rng.standard_normal((L, n, r))
+    a = np_(K.dot(Ai, Aj, Ax, x))
+    b = np_(K.dot(Ai, Aj, Ax, x))
+    assert np.array_equal(a, b)
+    assert np.all(a[:, n - 5:, :] == 0)
+    ref = np.zeros_like(x)
+    for m in range(L):
+        np.add.at(ref[m], Ai, Ax[m][:, None] * x[m][Aj])
+    assert relerr(a, ref) < 1e-13
+
+
 # ------------------------------------------------------------------ structural edge cases
 def _upper_triangular(n, dtype, L, seed=3):
     r = np.random.default_rng(seed)
