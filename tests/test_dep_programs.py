@@ -135,7 +135,8 @@ def test_panel_solve_reports_singular_and_keeps_status(K, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cplx,g,L,r", [(False, 36, 8, 256), (True, 36, 8, 256), (False, 20, 48, 48), (True, 16, 64, 33)])
+@pytest.mark.parametrize("cplx,g,L,r", [(False, 36, 8, 256), (True, 36, 8, 256), (False, 20, 48, 48), (True, 16, 64, 33),
+                                        (False, 16, 200, 16)])  # the last one: more systems than SMs (batch-interleaved values)
 def test_row_blocked_multi_rhs_solve_vs_oracle(K, oracle, monkeypatch, cplx, g, L, r):
     """lv_solve_grouped (plan.hpp: GroupProgram): many right-hand sides per system, rows of a
     supernode blocked in registers; solve and transpose solve against the oracle and against the plain
