@@ -3,17 +3,19 @@
 //
 // The level-scheduled kernels (kernels_level.cuh) pay a CTA barrier and a memory round trip per
 // level; a system whose elimination DAG is a long chain (cfg 4: circuit matrices, 5 215 levels to
-// factor, 6 205 per triangular solve) is then latency-bound at ~1.7 us per level.  Here nothing
-// waits for a level: the work is dealt to the warps of a persistent CTA in a fixed order that
-// respects the dependencies, and every unit waits only for the producers of its own operands,
-// through ready flags (and per-block counters) in shared memory.
+// factor, 6 205 per triangular solve) is then latency-bound at 1-2 us per level.  The kernels here
+// have no level barriers: the work runs in a fixed order that respects the dependencies, and a
+// unit waits only for the producers of its own operands.
 //
-//   dep_factor  left-looking refactorization, a warp per column (the shape of klu_refactor's
-//               own loop, reached from /root/reference/klujax.cpp:781, 911): the column lives in
-//               the warp's shared-memory buffer, every U(j,k) waits for column j's flag, the 32
-//               lanes subtract L(:,j)*U(j,k) (coalesced loads of L(:,j), 16-bit destination
-//               positions shared by the whole batch), then pivot reciprocal, scaling of L(:,k),
-//               the pivot-parity certificate, one coalesced store of the column, flag.
+//   dep_factor  (opt-in, KLUJAX_CUDA_DEP_FACTOR=1: correct, but slower than lv_factor on cfg 4 -
+//               profiles/dep_r02.md)  left-looking refactorization, a warp per column (the shape of
+//               klu_refactor's own loop, reached from /root/reference/klujax.cpp:781, 911): the
+//               column lives in the warp's shared-memory buffer, every U(j,k) waits for the ready
+//               flag of column j (device-side dependency flags in shared memory), the 32 lanes
+//               subtract L(:,j)*U(j,k) - the records of a column go in chunks of 32 whose
+//               destination positions and (for final columns) entries of L are staged with
+//               cp.async - then pivot reciprocal, scaling of L(:,k), the pivot-parity certificate,
+//               one coalesced store of the column, flag.
 //   panel_solve klu_solve / klu_tsolve (klujax.cpp:1087, 1220) as one sequential list of row
 //               tasks in panels of 32 (plan.hpp: PanelProgram): the right-hand side lives in shared
 //               memory, lane r owns task r of the panel, operands from earlier panels are plain

@@ -14,6 +14,11 @@
 // :1069-1076, :1095-1101 (there is no transposition pass here: the
 // permutations P, Q and the row scaling are folded into the load and the store
 // of X).  Also holds the batched COO SpMM twin of dot_* (klujax.cpp:165-249).
+//
+// Round 2: system-major value layout with a gather fill (lv_prepare_sysmajor) when a CTA owns one
+// system; the solves run on the caller's x; lv_solve_grouped blocks the rows of a supernode in
+// registers for many right-hand sides (plan.hpp: GroupProgram); when a CTA owns a single
+// right-hand-side column the solves go to panel_solve (kernels_dep.cuh).
 #pragma once
 #include <cuda_runtime.h>
 
